@@ -1,0 +1,157 @@
+// Shared device/host helpers for libtnb (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tnb.h"
+
+#define TNB_CUDA_CHECK(expr)                         \
+  do {                                               \
+    cudaError_t _e = (expr);                         \
+    if (_e != cudaSuccess) return (int)_e;           \
+  } while (0)
+
+// every kernel launch of the library goes through this macro, so the counter
+// is the number of libtnb kernels launched (bench.py reports it as gpu_launches)
+namespace tnb { extern long long g_launches; }
+#define TNB_LAUNCH_CHECK()                   \
+  do {                                       \
+    ++tnb::g_launches;                       \
+    TNB_CUDA_CHECK(cudaGetLastError());      \
+  } while (0)
+
+namespace tnb {
+
+typedef double2 cplx;  // interleaved complex128
+
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+// a + conj(x)*y
+__host__ __device__ __forceinline__ cplx cfma_conj(cplx x, cplx y, cplx a) {
+  return make_double2(a.x + x.x * y.x + x.y * y.y, a.y + x.x * y.y - x.y * y.x);
+}
+// a + x*y
+__host__ __device__ __forceinline__ cplx cfma(cplx x, cplx y, cplx a) {
+  return make_double2(a.x + x.x * y.x - x.y * y.y, a.y + x.x * y.y + x.y * y.x);
+}
+__host__ __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+
+// Scalar traits so kernels can be written once for double and complex128.
+template <typename T> struct Num;
+template <> struct Num<double> {
+  static constexpr int dtype = TNB_F64;
+  __host__ __device__ static double zero() { return 0.0; }
+  __host__ __device__ static double one() { return 1.0; }
+  __host__ __device__ static double conj(double a) { return a; }
+  __host__ __device__ static double mul(double a, double b) { return a * b; }
+  __host__ __device__ static double add(double a, double b) { return a + b; }
+  __host__ __device__ static double sub(double a, double b) { return a - b; }
+  __host__ __device__ static double scale(double a, double s) { return a * s; }
+  __host__ __device__ static double abs2(double a) { return a * a; }
+  __host__ __device__ static double real(double a) { return a; }
+  __host__ __device__ static double from(double re, double) { return re; }
+  __host__ __device__ static double fma_conj(double x, double y, double a) { return a + x * y; }
+  __host__ __device__ static double fma(double x, double y, double a) { return a + x * y; }
+};
+template <> struct Num<cplx> {
+  static constexpr int dtype = TNB_C128;
+  __host__ __device__ static cplx zero() { return make_double2(0.0, 0.0); }
+  __host__ __device__ static cplx one() { return make_double2(1.0, 0.0); }
+  __host__ __device__ static cplx conj(cplx a) { return cconj(a); }
+  __host__ __device__ static cplx mul(cplx a, cplx b) { return cmul(a, b); }
+  __host__ __device__ static cplx add(cplx a, cplx b) { return cadd(a, b); }
+  __host__ __device__ static cplx sub(cplx a, cplx b) { return csub(a, b); }
+  __host__ __device__ static cplx scale(cplx a, double s) { return cscale(a, s); }
+  __host__ __device__ static double abs2(cplx a) { return cabs2(a); }
+  __host__ __device__ static double real(cplx a) { return a.x; }
+  __host__ __device__ static cplx from(double re, double im) { return make_double2(re, im); }
+  __host__ __device__ static cplx fma_conj(cplx x, cplx y, cplx a) { return cfma_conj(x, y, a); }
+  __host__ __device__ static cplx fma(cplx x, cplx y, cplx a) { return cfma(x, y, a); }
+};
+
+static inline size_t elem_size(int dtype) { return dtype == TNB_C128 ? 16 : 8; }
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+// cp.async with zero-fill: copies src_bytes (<= CP) and zero-fills the rest.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+// D(8x8) += A(8x4, row) * B(4x8, col): one DMMA.8x8x4 on sm_100a.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- collapsed strided view used by permute / elementwise kernels ------------
+struct View {
+  int rank;
+  int64_t shape[TNB_MAX_RANK];
+  int64_t stride[TNB_MAX_RANK];
+  int64_t numel;
+};
+
+// Drop size-1 axes and merge axes that are contiguous with respect to each
+// other (stride[i] == stride[i+1]*shape[i+1]); logical (row-major) order kept.
+static inline View collapse(int rank, const int64_t* shape, const int64_t* stride) {
+  View v;
+  v.rank = 0;
+  v.numel = 1;
+  for (int i = 0; i < rank; ++i) {
+    v.numel *= shape[i];
+    if (shape[i] == 1) continue;
+    if (v.rank > 0 && v.stride[v.rank - 1] == stride[i] * shape[i]) {
+      v.shape[v.rank - 1] *= shape[i];
+      v.stride[v.rank - 1] = stride[i];
+    } else {
+      v.shape[v.rank] = shape[i];
+      v.stride[v.rank] = stride[i];
+      v.rank++;
+    }
+  }
+  if (v.rank == 0) {
+    v.rank = 1;
+    v.shape[0] = 1;
+    v.stride[0] = 1;
+  }
+  return v;
+}
+
+static inline bool valid_tensor(const tnb_tensor_t* t) {
+  if (!t || t->rank < 0 || t->rank > TNB_MAX_RANK) return false;
+  if (t->dtype != TNB_F64 && t->dtype != TNB_C128) return false;
+  for (int i = 0; i < t->rank; ++i)
+    if (t->shape[i] < 0) return false;
+  return true;
+}
+static inline int64_t numel(const tnb_tensor_t* t) {
+  int64_t n = 1;
+  for (int i = 0; i < t->rank; ++i) n *= t->shape[i];
+  return n;
+}
+
+int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+}  // namespace tnb

@@ -1,0 +1,334 @@
+// FP64 / complex128 GEMM on the sm_100a FP64 tensor pipe (DMMA.8x8x4).
+//
+//   C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b]        (row-major)
+//
+// tcgen05.mma has no f64 kind, so FP64 tensor math on Blackwell is
+// mma.sync.m8n8k4.f64 (one DMMA.8x8x4 per instruction).  Layout of one CTA:
+//   * real:    128x128 C tile, 8 warps (2 x 4), warp tile 64x32, BK = 16
+//   * complex: 128x64  C tile, 8 warps (4 x 2), warp tile 32x32, BK = 8,
+//              4 DMMAs per (m8,n8,k4) tile pair: re += ar*br, re += (-ai)*bi,
+//              im += ar*bi, im += ai*br (interleaved re/im stays interleaved in
+//              shared memory; fragments are 16-byte LDS)
+//   * a "small" variant (64x64 real / 64x32 complex, 4 warps) for skinny shapes
+// Operands are staged by a 4-stage cp.async (LDGSTS, 16-byte, zero-fill at the
+// edges) pipeline.  Either operand may be K-contiguous ([mn][k]) or
+// MN-contiguous ([k][mn]) in global memory -- this is how the label->axis
+// permutation of np.tensordot is folded into operand staging instead of being
+// materialised -- and the shared-memory row pitch is padded so that the
+// per-lane fragment loads (row = lane/4, k = lane%4) are bank-conflict free:
+//   K-contiguous : pitch BK+4 (real) / BK+4 (complex)
+//   MN-contiguous: pitch BMN+4 (real) / BMN+2 (complex)
+// Conjugation of either operand is a sign flip on the imaginary fragment.
+// Algorithmic work: 2*M*N*K flop (real), 8*M*N*K flop (complex).
+#include "common.cuh"
+
+namespace tnb {
+
+struct GemmArgs {
+  const void* A;
+  const void* B;
+  void* C;
+  int64_t M, N, K;
+  int64_t lda, ldb, ldc;
+  int64_t sA, sB, sC;  // batch strides (elements)
+  double alpha_r, alpha_i, beta_r, beta_i;
+  int conjA, conjB;
+  int tiles_m, tiles_n;
+};
+
+template <bool CPLX, bool SMALL> struct Cfg;
+template <> struct Cfg<false, false> { static constexpr int BM = 128, BN = 128, BK = 16, WM = 64, WN = 32, WARPS_M = 2, WARPS_N = 4; };
+template <> struct Cfg<false, true>  { static constexpr int BM = 64,  BN = 64,  BK = 16, WM = 32, WN = 32, WARPS_M = 2, WARPS_N = 2; };
+template <> struct Cfg<true, false>  { static constexpr int BM = 128, BN = 64,  BK = 8,  WM = 32, WN = 32, WARPS_M = 4, WARPS_N = 2; };
+template <> struct Cfg<true, true>   { static constexpr int BM = 64,  BN = 32,  BK = 8,  WM = 32, WN = 16, WARPS_M = 2, WARPS_N = 2; };
+
+constexpr int STAGES = 4;
+
+template <bool CPLX, bool KC, int BMN, int BK> struct TileLayout {
+  // pitch in elements
+  static constexpr int PITCH = KC ? (BK + 4) : (BMN + (CPLX ? 2 : 4));
+  static constexpr int ROWS = KC ? BMN : BK;
+  static constexpr int ELEMS = ROWS * PITCH;
+};
+
+// Stage one operand tile (BMN x BK logical) into shared memory.
+//   KC  : global is [mn][k] with k contiguous  -> smem [mn][k]
+//   !KC : global is [k][mn] with mn contiguous -> smem [k][mn]
+// VEC (real only): 16-byte packets of two doubles; requires even ld / offsets
+// and a 16-byte aligned base.  Complex elements are always 16-byte packets.
+template <typename T, bool CPLX, bool KC, bool VEC, int BMN, int BK, int THREADS>
+__device__ __forceinline__ void load_tile(T* smem, const T* __restrict__ g, int64_t ld, int64_t mn0, int64_t k0,
+                                          int64_t MN, int64_t K, int tid) {
+  typedef TileLayout<CPLX, KC, BMN, BK> L;
+  constexpr int EPP = CPLX ? 1 : (VEC ? 2 : 1);  // elements per packet
+  constexpr int INNER = KC ? BK : BMN;           // contiguous extent
+  constexpr int OUTER = KC ? BMN : BK;
+  constexpr int PPR = INNER / EPP;               // packets per row
+  constexpr int TOTAL = OUTER * PPR;
+  const int64_t in_lim = KC ? K : MN, out_lim = KC ? MN : K;
+  const int64_t in0 = KC ? k0 : mn0, out0 = KC ? mn0 : k0;
+#pragma unroll
+  for (int it = 0; it < (TOTAL + THREADS - 1) / THREADS; ++it) {
+    const int c = tid + it * THREADS;
+    if (TOTAL % THREADS != 0 && c >= TOTAL) break;
+    const int r = c / PPR, p = (c - r * PPR) * EPP;
+    const int64_t go = out0 + r, gi = in0 + p;
+    T* dst = smem + r * L::PITCH + p;
+    int64_t valid = (go < out_lim) ? (in_lim - gi) : 0;
+    if (valid > EPP) valid = EPP;
+    if (valid < 0) valid = 0;
+    // keep the source address in-bounds even when nothing is copied
+    const T* src = (valid > 0) ? (g + go * ld + gi) : g;
+    if constexpr (sizeof(T) * EPP == 16) cp_async16(dst, src, (int)valid * (int)sizeof(T));
+    else cp_async8(dst, src, (int)valid * (int)sizeof(T));
+  }
+}
+
+template <bool CPLX, bool SMALL, bool A_KC, bool B_KC, bool VEC>
+__global__ void __launch_bounds__(Cfg<CPLX, SMALL>::WARPS_M * Cfg<CPLX, SMALL>::WARPS_N * 32)
+gemm_kernel(GemmArgs g) {
+  typedef Cfg<CPLX, SMALL> C_;
+  typedef typename std::conditional<CPLX, double2, double>::type T;
+  constexpr int BM = C_::BM, BN = C_::BN, BK = C_::BK, WM = C_::WM, WN = C_::WN;
+  constexpr int THREADS = C_::WARPS_M * C_::WARPS_N * 32;
+  constexpr int MT = WM / 8, NT = WN / 8;
+  typedef TileLayout<CPLX, A_KC, BM, BK> LA;
+  typedef TileLayout<CPLX, B_KC, BN, BK> LB;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sA = reinterpret_cast<T*>(smem_raw);
+  T* sB = sA + STAGES * LA::ELEMS;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;  // fragment row / k index
+  const int wm = warp / C_::WARPS_N, wn = warp % C_::WARPS_N;
+
+  // tile coordinates: consecutive CTAs walk down M first so that the B tile
+  // (shared by a column of C tiles) stays hot in L2
+  const int tile = blockIdx.x;
+  const int tm = tile % g.tiles_m, tn = tile / g.tiles_m;
+  const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+  const int64_t bz = blockIdx.y;
+  const T* A = reinterpret_cast<const T*>(g.A) + bz * g.sA;
+  const T* B = reinterpret_cast<const T*>(g.B) + bz * g.sB;
+  T* Cg = reinterpret_cast<T*>(g.C) + bz * g.sC;
+
+  double acc[MT][NT][CPLX ? 4 : 2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[i][j][r] = 0.0;
+
+  const int KT = (int)((g.K + BK - 1) / BK);
+
+  auto issue = [&](int kt) {
+    if (kt < KT) {
+      const int s = kt % STAGES;
+      load_tile<T, CPLX, A_KC, VEC, BM, BK, THREADS>(sA + s * LA::ELEMS, A, g.lda, m0, (int64_t)kt * BK, g.M, g.K, tid);
+      load_tile<T, CPLX, B_KC, VEC, BN, BK, THREADS>(sB + s * LB::ELEMS, B, g.ldb, n0, (int64_t)kt * BK, g.N, g.K, tid);
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+  const double sgnA = g.conjA ? -1.0 : 1.0, sgnB = g.conjB ? -1.0 : 1.0;
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(kt + STAGES - 1);
+    const T* a_s = sA + (kt % STAGES) * LA::ELEMS;
+    const T* b_s = sB + (kt % STAGES) * LB::ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      T af[MT], bf[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int m = wm * WM + i * 8 + gq, k = kk + tq;
+        af[i] = A_KC ? a_s[m * LA::PITCH + k] : a_s[k * LA::PITCH + m];
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int n = wn * WN + j * 8 + gq, k = kk + tq;
+        bf[j] = B_KC ? b_s[n * LB::PITCH + k] : b_s[k * LB::PITCH + n];
+      }
+      if constexpr (!CPLX) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      } else {
+        double nai[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) { af[i].y *= sgnA; nai[i] = -af[i].y; }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) bf[j].y *= sgnB;
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);  // re += ar*br
+            dmma884(acc[i][j][2], acc[i][j][3], af[i].x, bf[j].y);  // im += ar*bi
+            dmma884(acc[i][j][0], acc[i][j][1], nai[i], bf[j].y);   // re -= ai*bi
+            dmma884(acc[i][j][2], acc[i][j][3], af[i].y, bf[j].x);  // im += ai*br
+          }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: thread owns C[row = gq][cols 2*tq, 2*tq+1] of every 8x8 tile
+  const bool has_beta = (g.beta_r != 0.0 || g.beta_i != 0.0);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int64_t row = m0 + wm * WM + i * 8 + gq;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int64_t col = n0 + wn * WN + j * 8 + 2 * tq;
+      if (col >= g.N) continue;
+      T* dst = Cg + row * g.ldc + col;
+      if constexpr (!CPLX) {
+        double v0 = g.alpha_r * acc[i][j][0], v1 = g.alpha_r * acc[i][j][1];
+        if (has_beta) {
+          v0 += g.beta_r * dst[0];
+          if (col + 1 < g.N) v1 += g.beta_r * dst[1];
+        }
+        if (col + 1 < g.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+        } else {
+          dst[0] = v0;
+          if (col + 1 < g.N) dst[1] = v1;
+        }
+      } else {
+        const double2 al = make_double2(g.alpha_r, g.alpha_i), be = make_double2(g.beta_r, g.beta_i);
+        double2 v0 = cmul(al, make_double2(acc[i][j][0], acc[i][j][2]));
+        double2 v1 = cmul(al, make_double2(acc[i][j][1], acc[i][j][3]));
+        if (has_beta) {
+          v0 = cadd(v0, cmul(be, dst[0]));
+          if (col + 1 < g.N) v1 = cadd(v1, cmul(be, dst[1]));
+        }
+        dst[0] = v0;
+        if (col + 1 < g.N) dst[1] = v1;
+      }
+    }
+  }
+}
+
+template <bool CPLX, bool SMALL, bool A_KC, bool B_KC, bool VEC>
+static int launch_gemm(GemmArgs& g, int64_t batch, cudaStream_t st) {
+  typedef Cfg<CPLX, SMALL> C_;
+  typedef TileLayout<CPLX, A_KC, C_::BM, C_::BK> LA;
+  typedef TileLayout<CPLX, B_KC, C_::BN, C_::BK> LB;
+  constexpr size_t ES = CPLX ? 16 : 8;
+  constexpr size_t smem = (size_t)STAGES * (LA::ELEMS + LB::ELEMS) * ES;
+  auto kern = gemm_kernel<CPLX, SMALL, A_KC, B_KC, VEC>;
+  static bool configured = false;
+  if (!configured) {
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  g.tiles_m = (int)((g.M + C_::BM - 1) / C_::BM);
+  g.tiles_n = (int)((g.N + C_::BN - 1) / C_::BN);
+  const int threads = C_::WARPS_M * C_::WARPS_N * 32;
+  // grid.y carries the batch (<= 65535 per launch)
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int64_t nb = (batch - b0 < 65535) ? (batch - b0) : 65535;
+    GemmArgs h = g;
+    h.A = (const char*)g.A + b0 * g.sA * ES;
+    h.B = (const char*)g.B + b0 * g.sB * ES;
+    h.C = (char*)g.C + b0 * g.sC * ES;
+    dim3 grid((unsigned)(g.tiles_m * g.tiles_n), (unsigned)nb);
+    kern<<<grid, threads, smem, st>>>(h);
+    TNB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+template <bool CPLX, bool SMALL, bool VEC>
+static int dispatch_layout(GemmArgs& g, bool a_kc, bool b_kc, int64_t batch, cudaStream_t st) {
+  if (a_kc && b_kc) return launch_gemm<CPLX, SMALL, true, true, VEC>(g, batch, st);
+  if (a_kc && !b_kc) return launch_gemm<CPLX, SMALL, true, false, VEC>(g, batch, st);
+  if (!a_kc && b_kc) return launch_gemm<CPLX, SMALL, false, true, VEC>(g, batch, st);
+  return launch_gemm<CPLX, SMALL, false, false, VEC>(g, batch, st);
+}
+
+// C := beta*C when K == 0 or alpha == 0 (BLAS semantics)
+template <typename T>
+__global__ void scale_c_kernel(T* C, int64_t M, int64_t N, int64_t ldc, int64_t sC, double br, double bi) {
+  T* c = C + (int64_t)blockIdx.y * sC;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += step) {
+    const int64_t r = i / N, col = i - r * N;
+    T& x = c[r * ldc + col];
+    if (br == 0.0 && bi == 0.0) x = Num<T>::zero();
+    else if constexpr (sizeof(T) == 8) x = x * br;
+    else x = cmul(x, make_double2(br, bi));
+  }
+}
+
+int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
+         int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
+         int64_t sC, int64_t batch, cudaStream_t st) {
+  if (M < 0 || N < 0 || K < 0 || batch < 0) return TNB_E_ARG;
+  if (M == 0 || N == 0 || batch == 0) return 0;
+  if (!C) return TNB_E_ARG;
+  const bool cplx = (dtype == TNB_C128);
+  if (!cplx && dtype != TNB_F64) return TNB_E_ARG;
+  if (!cplx && (ai != 0.0 || bi != 0.0)) return TNB_E_ARG;
+  if (K == 0 || (ar == 0.0 && ai == 0.0)) {
+    if (br == 1.0 && bi == 0.0) return 0;
+    int64_t blocks = (M * N + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+      const int64_t nb = (batch - b0 < 65535) ? (batch - b0) : 65535;
+      dim3 grid((unsigned)blocks, (unsigned)nb);
+      if (cplx) scale_c_kernel<double2><<<grid, 256, 0, st>>>((double2*)C + b0 * sC, M, N, ldc, sC, br, bi);
+      else scale_c_kernel<double><<<grid, 256, 0, st>>>((double*)C + b0 * sC, M, N, ldc, sC, br, bi);
+      TNB_LAUNCH_CHECK();
+    }
+    return 0;
+  }
+  if (!A || !B) return TNB_E_ARG;
+  GemmArgs g;
+  g.A = A; g.B = B; g.C = C;
+  g.M = M; g.N = N; g.K = K;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.sA = sA; g.sB = sB; g.sC = sC;
+  g.alpha_r = ar; g.alpha_i = ai; g.beta_r = br; g.beta_i = bi;
+  g.conjA = cplx && (opA == TNB_OP_C || opA == TNB_OP_J);
+  g.conjB = cplx && (opB == TNB_OP_C || opB == TNB_OP_J);
+  // op N on A: stored M x K (k contiguous). op T/C: stored K x M (m contiguous).
+  const bool a_kc = (opA == TNB_OP_N || opA == TNB_OP_J);
+  // op N on B: stored K x N (n contiguous). op T/C: stored N x K (k contiguous).
+  const bool b_kc = !(opB == TNB_OP_N || opB == TNB_OP_J);
+  // skinny problems: smaller tiles waste fewer DMMAs and fill more SMs
+  const int64_t big_tiles = cplx ? ((M + 127) / 128) * ((N + 63) / 64) : ((M + 127) / 128) * ((N + 127) / 128);
+  const bool small = (M <= 64) || (N <= (cplx ? 32 : 64)) || (big_tiles * batch < (int64_t)sm_count());
+  if (cplx) {
+    return small ? dispatch_layout<true, true, true>(g, a_kc, b_kc, batch, st)
+                 : dispatch_layout<true, false, true>(g, a_kc, b_kc, batch, st);
+  }
+  const bool vec = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
+                   (sA % 2 == 0 || batch == 1) && (sB % 2 == 0 || batch == 1);
+  if (vec)
+    return small ? dispatch_layout<false, true, true>(g, a_kc, b_kc, batch, st)
+                 : dispatch_layout<false, false, true>(g, a_kc, b_kc, batch, st);
+  return small ? dispatch_layout<false, true, false>(g, a_kc, b_kc, batch, st)
+               : dispatch_layout<false, false, false>(g, a_kc, b_kc, batch, st);
+}
+
+}  // namespace tnb
+
+extern "C" int tnb_gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, const double* alpha,
+                        const void* A, int64_t lda, int64_t strideA, const void* B, int64_t ldb, int64_t strideB,
+                        const double* beta, void* C, int64_t ldc, int64_t strideC, int64_t batch, void* stream) {
+  if (!alpha || !beta) return TNB_E_ARG;
+  if (opA < 0 || opA > 3 || opB < 0 || opB > 3) return TNB_E_ARG;
+  return tnb::gemm(dtype, opA, opB, M, N, K, alpha[0], alpha[1], A, lda, strideA, B, ldb, strideB, beta[0], beta[1],
+                   C, ldc, strideC, batch, (cudaStream_t)stream);
+}

@@ -1,0 +1,423 @@
+// Reduced QR factorisation (np.linalg.qr(mode="reduced"), reference call site
+// tensor.py:1044) for float64 / complex128, LAPACK geqrf/ungqr conventions:
+// H_j = I - tau_j v_j v_j^H, R = H_k^H ... H_1^H A with a REAL diagonal,
+// Q = H_1 ... H_k [I; 0].
+//
+// Blocked Householder with compact-WY updates:
+//   * panel (NB = 32 columns): ONE thread-block cluster owns the whole panel in
+//     shared memory, rows split across the CTAs of the cluster.  Per column the
+//     only communication is one all-reduce of the NB partial dot products
+//     x^H A[:, c] (from which norm, tau, and v^H A[:, c] all follow), exchanged
+//     through distributed shared memory with one cluster barrier -- no global
+//     memory round trip, no grid-wide sync.  The panel also emits V (explicit,
+//     unit lower trapezoid) and the triangular factor T of the block reflector.
+//   * trailing matrix / explicit Q: three GEMMs per panel on the FP64 tensor
+//     pipe (gemm.cu): W = V^H A2, W = T^H W, A2 -= V W.
+// Nominal flops (LAPACK model): 2(2mn^2 - 2/3 n^3) real, x4 complex.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tnb {
+
+int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
+         int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
+         int64_t sC, int64_t batch, cudaStream_t st);
+
+constexpr int QR_NB = 32;
+constexpr int QR_THREADS = 256;
+constexpr int QR_WARPS = QR_THREADS / 32;
+
+struct QrPanelArgs {
+  void* W;        // working copy of A, m x n, ld = ldw
+  void* V;        // explicit Householder vectors, m x k, ld = ldv
+  void* T;        // this panel's jb x jb triangular factor (row-major, ld = QR_NB)
+  int64_t m, ldw, ldv;
+  int64_t j0;     // first column / diagonal row of the panel
+  int jb;         // panel width (<= QR_NB)
+  int rows_per;   // panel rows owned by each CTA of the cluster
+  int pitch;      // shared-memory pitch of one panel column (elements)
+};
+
+template <typename T> __device__ __forceinline__ T warp_sum_t(T v);
+template <> __device__ __forceinline__ double warp_sum_t<double>(double v) { return warp_sum(v); }
+template <> __device__ __forceinline__ cplx warp_sum_t<cplx>(cplx v) {
+  return make_double2(warp_sum(v.x), warp_sum(v.y));
+}
+
+// Shared-memory layout (dynamic):
+//   P    [jb][pitch]      panel slab, column-major (column c contiguous over the CTA's rows)
+//   part [2][QR_NB]       this CTA's partial dots, double-buffered by column parity
+//   rowv [2][QR_NB]       the diagonal row A[j, c] (written by the CTA that owns row j)
+//   tau  [QR_NB]
+//   Z    [QR_NB][QR_NB]   partial V^H V, later T
+template <typename T>
+__global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
+  typedef Num<T> N_;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* P = reinterpret_cast<T*>(smem_raw);
+  T* part = P + (size_t)QR_NB * a.pitch;
+  T* rowv = part + 2 * QR_NB;
+  T* tau = rowv + 2 * QR_NB;
+  T* Z = tau + QR_NB;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int jb = a.jb;
+  const int64_t mr = a.m - a.j0;                 // rows in the panel
+  const int64_t r_lo = (int64_t)crank * a.rows_per;  // first panel row of this CTA
+  int nrows = (int)((mr - r_lo < a.rows_per) ? (mr - r_lo) : a.rows_per);
+  if (nrows < 0) nrows = 0;
+  T* Wg = reinterpret_cast<T*>(a.W);
+  T* Vg = reinterpret_cast<T*>(a.V);
+
+  // ---- load the slab (global rows are contiguous along c) --------------------------
+  for (int i = tid; i < nrows * jb; i += QR_THREADS) {
+    const int r = i / jb, c = i - r * jb;
+    P[c * a.pitch + r] = Wg[(a.j0 + r_lo + r) * a.ldw + a.j0 + c];
+  }
+  __syncthreads();
+
+  for (int j = 0; j < jb; ++j) {
+    const int buf = j & 1;
+    // local index of the first row at or below the diagonal
+    int lo = (int)(j - r_lo);
+    if (lo < 0) lo = 0;
+    const bool own_diag = (j >= r_lo && j < r_lo + nrows);
+    const int jl = (int)(j - r_lo);  // local row of the diagonal (valid if own_diag)
+    // ---- partial dots d_c = sum_{r >= j} conj(x_r) A[r, c], c = j..jb-1 ---------------
+    for (int c = j + warp; c < jb; c += QR_WARPS) {
+      T acc = N_::zero();
+      const T* xj = P + j * a.pitch;
+      const T* xc = P + c * a.pitch;
+      for (int r = lo + lane; r < nrows; r += 32) acc = N_::fma_conj(xj[r], xc[r], acc);
+      acc = warp_sum_t<T>(acc);
+      if (lane == 0) {
+        part[buf * QR_NB + c] = acc;
+        if (own_diag) rowv[buf * QR_NB + c] = xc[jl];
+      }
+    }
+    cluster.sync();
+    // ---- every CTA forms the same reflector parameters -------------------------------------
+    const int owner = (int)(j / a.rows_per);
+    const T* rowv_owner = cluster.map_shared_rank(rowv, owner);
+    // column j's total first (all warps need it)
+    T dj = N_::zero();
+    if (lane < C) dj = cluster.map_shared_rank(part, lane)[buf * QR_NB + j];
+    dj = warp_sum_t<T>(dj);
+    const T alpha = rowv_owner[buf * QR_NB + j];
+    const double normx2 = N_::real(dj);
+    const bool no_tail = (a.j0 + j == a.m - 1);
+    double beta;
+    T tau_j, scale;  // v = x * scale below the diagonal
+    double alpha_im = 0.0;
+    if constexpr (sizeof(T) == 16) alpha_im = alpha.y;
+    if (normx2 == 0.0 || (no_tail && alpha_im == 0.0)) {
+      beta = N_::real(alpha);
+      tau_j = N_::zero();
+      scale = N_::zero();
+    } else {
+      beta = -copysign(sqrt(normx2), N_::real(alpha));
+      const double ib = 1.0 / beta;
+      tau_j = N_::from((beta - N_::real(alpha)) * ib, -alpha_im * ib);
+      // scale = 1 / (alpha - beta)
+      const double dr = N_::real(alpha) - beta;
+      const double den = dr * dr + alpha_im * alpha_im;
+      scale = N_::from(dr / den, -alpha_im / den);
+    }
+    if (tid == 0) tau[j] = tau_j;
+    const bool active = !(N_::real(tau_j) == 0.0 && N_::abs2(tau_j) == 0.0);
+    // ---- C1: x -> v on column j (all threads over rows), diagonal := beta ------------------
+    {
+      T* xj = P + j * a.pitch;
+      const int lo1 = own_diag ? jl + 1 : lo;
+      for (int r = lo1 + tid; r < nrows; r += QR_THREADS) xj[r] = N_::mul(xj[r], scale);
+      if (own_diag && tid == 0) xj[jl] = N_::from(beta, 0.0);
+    }
+    __syncthreads();
+    // ---- C2: A[:, c] -= conj(tau) * (v^H A[:, c]) * v, c > j ---------------------------------
+    if (active) {
+      for (int c = j + 1 + warp; c < jb; c += QR_WARPS) {
+        T dc = N_::zero();
+        if (lane < C) dc = cluster.map_shared_rank(part, lane)[buf * QR_NB + c];
+        dc = warp_sum_t<T>(dc);
+        const T ajc = rowv_owner[buf * QR_NB + c];
+        // w = v^H A_c = A[j,c] + conj(scale) * (d_c - conj(alpha) * A[j,c])
+        const T t1 = N_::sub(dc, N_::mul(N_::conj(alpha), ajc));
+        const T w = N_::add(ajc, N_::mul(N_::conj(scale), t1));
+        const T f = N_::mul(N_::conj(tau_j), w);
+        const T* vj = P + j * a.pitch;
+        T* xc = P + c * a.pitch;
+        const int lo1 = own_diag ? jl + 1 : lo;
+        for (int r = lo1 + lane; r < nrows; r += 32) xc[r] = N_::sub(xc[r], N_::mul(f, vj[r]));
+        if (own_diag && lane == 0) xc[jl] = N_::sub(xc[jl], f);  // v_j = 1 on the diagonal
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- T factor: Z = strictly-upper part of V^H V, reduced over the cluster --------------------
+  for (int idx = warp; idx < jb * jb; idx += QR_WARPS) {
+    const int i = idx / jb, c = idx - i * jb;
+    if (i >= c) { if (lane == 0) Z[i * QR_NB + c] = N_::zero(); continue; }
+    // v_i^H v_c over rows r > c (both below their diagonals), plus row c where v_c = 1
+    T acc = N_::zero();
+    int lo = (int)(c + 1 - r_lo);
+    if (lo < 0) lo = 0;
+    const T* vi = P + i * a.pitch;
+    const T* vc = P + c * a.pitch;
+    for (int r = lo + lane; r < nrows; r += 32) acc = N_::fma_conj(vi[r], vc[r], acc);
+    acc = warp_sum_t<T>(acc);
+    if (lane == 0) {
+      const int cl = (int)(c - r_lo);
+      if (cl >= 0 && cl < nrows) acc = N_::add(acc, N_::conj(vi[cl]));
+      Z[i * QR_NB + c] = acc;
+    }
+  }
+  cluster.sync();
+  if (crank == 0) {
+    for (int idx = tid; idx < jb * jb; idx += QR_THREADS) {
+      const int i = idx / jb, c = idx - i * jb;
+      if (i >= c) continue;
+      T s = N_::zero();
+      for (int q = 0; q < C; ++q) s = N_::add(s, cluster.map_shared_rank(Z, q)[i * QR_NB + c]);
+      Z[i * QR_NB + c] = s;  // only CTA 0's copy holds the total; the others are just read
+    }
+  }
+  cluster.sync();  // totals complete, and no CTA exits while its Z is still being read
+  if (crank == 0 && warp == 0) {
+    // T is upper triangular (LAPACK larft, forward/columnwise):
+    //   T[c][c] = tau_c,  T[0:c, c] = -tau_c * T[0:c, 0:c] * z[0:c, c].
+    // It is built in Z's lower triangle, transposed: T[i][c] lives at Z[c][i], i <= c;
+    // the strictly upper part of Z keeps z.
+    for (int c = 0; c < jb; ++c) {
+      const T tc = tau[c];
+      T mine = N_::zero();
+      if (lane < c) {
+        T s = N_::zero();
+        for (int q = lane; q < c; ++q) s = N_::add(s, N_::mul(Z[q * QR_NB + lane], Z[q * QR_NB + c]));
+        mine = N_::mul(N_::sub(N_::zero(), tc), s);
+      }
+      __syncwarp();
+      if (lane < c) Z[c * QR_NB + lane] = mine;
+      if (lane == c) Z[c * QR_NB + c] = tc;
+      __syncwarp();
+    }
+    T* Tg = reinterpret_cast<T*>(a.T);
+    for (int idx = lane; idx < QR_NB * QR_NB; idx += 32) {
+      const int i = idx / QR_NB, c = idx - i * QR_NB;
+      T v = N_::zero();
+      if (i <= c && c < jb) v = Z[c * QR_NB + i];
+      Tg[idx] = v;
+    }
+  }
+
+  // ---- write back: R entries of the first jb rows, explicit V for every row ----------------------
+  for (int i = tid; i < nrows * jb; i += QR_THREADS) {
+    const int r = i / jb, c = i - r * jb;
+    const int64_t pr = r_lo + r;  // panel row
+    const T val = P[c * a.pitch + r];
+    if (pr <= c) Wg[(a.j0 + pr) * a.ldw + a.j0 + c] = val;
+    T v = N_::zero();
+    if (pr > c) v = val;
+    else if (pr == c) v = N_::one();
+    Vg[(a.j0 + pr) * a.ldv + a.j0 + c] = v;
+  }
+}
+
+// copy A (lda) -> W (ldw), contiguous rows
+template <typename T>
+__global__ void copy2d_kernel(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows, int64_t cols) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += step) {
+    const int64_t r = i / cols, c = i - r * cols;
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+// R = triu(W[0:k, 0:n])
+template <typename T>
+__global__ void extract_r_kernel(const T* W, int64_t ldw, T* R, int64_t k, int64_t n) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k * n; i += step) {
+    const int64_t r = i / n, c = i - r * n;
+    R[i] = (c >= r) ? W[r * ldw + c] : Num<T>::zero();
+  }
+}
+// Q := [I_k; 0] (m x k, ld)
+template <typename T>
+__global__ void eye_kernel(T* Q, int64_t m, int64_t k, int64_t ld) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m * k; i += step) {
+    const int64_t r = i / k, c = i - r * k;
+    Q[r * ld + c] = (r == c) ? Num<T>::one() : Num<T>::zero();
+  }
+}
+
+static inline unsigned blocks_for(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct QrLayout {
+  int64_t k, ldw, ldv, npanels;
+  size_t off_w, off_v, off_t, off_w1, off_w2, total;
+};
+
+static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
+  QrLayout L;
+  const size_t es = elem_size(dtype);
+  L.k = m < n ? m : n;
+  L.ldw = (n + 1) & ~(int64_t)1;
+  L.ldv = (L.k + 1) & ~(int64_t)1;
+  L.npanels = (L.k + QR_NB - 1) / QR_NB;
+  const int64_t wide = (n > L.k ? n : L.k);
+  size_t o = 0;
+  L.off_w = o;  o += align_up((size_t)m * L.ldw * es);
+  L.off_v = o;  o += align_up((size_t)m * L.ldv * es);
+  L.off_t = o;  o += align_up((size_t)L.npanels * QR_NB * QR_NB * es);
+  L.off_w1 = o; o += align_up((size_t)QR_NB * (wide + 2) * es);
+  L.off_w2 = o; o += align_up((size_t)QR_NB * (wide + 2) * es);
+  L.total = o;
+  return L;
+}
+
+template <typename T>
+static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
+  const int64_t mr = a.m - a.j0;
+  // smallest cluster whose slabs fit in shared memory (cap 200 KB per CTA)
+  const size_t fixed = (size_t)(2 * QR_NB + 2 * QR_NB + QR_NB + QR_NB * QR_NB) * sizeof(T);
+  int C = 1;
+  int rows_per = 0, pitch = 0;
+  size_t smem = 0;
+  for (;; C *= 2) {
+    rows_per = (int)((mr + C - 1) / C);
+    pitch = rows_per | 1;  // odd pitch: the transposing load is conflict-free
+    smem = (size_t)QR_NB * pitch * sizeof(T) + fixed;
+    if (smem <= 200 * 1024) break;
+    if (C >= 16) return TNB_E_UNSUPPORTED;  // panel taller than 16 CTAs can hold
+  }
+  a.rows_per = rows_per;
+  a.pitch = pitch;
+  auto kern = qr_panel_kernel<T>;
+  static size_t configured_smem = 0;
+  static bool nonportable = false;
+  if (smem > configured_smem) {
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 1024)));
+    configured_smem = 201 * 1024;
+  }
+  if (C > 8 && !nonportable) {
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    nonportable = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C, 1, 1);
+  cfg.blockDim = dim3(QR_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+  ++g_launches;
+  return 0;
+}
+
+template <typename T>
+static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws,
+                   cudaStream_t st) {
+  const QrLayout L = qr_layout(dtype, m, n);
+  char* base = (char*)ws;
+  T* W = (T*)(base + L.off_w);
+  T* V = (T*)(base + L.off_v);
+  T* Tb = (T*)(base + L.off_t);
+  T* W1 = (T*)(base + L.off_w1);
+  T* W2 = (T*)(base + L.off_w2);
+  const int64_t k = L.k;
+  copy2d_kernel<T><<<blocks_for(m * n), 256, 0, st>>>((const T*)A, lda, W, L.ldw, m, n);
+  TNB_LAUNCH_CHECK();
+  // V must be zero outside the panels' own columns/rows it writes (rows above a panel)
+  TNB_CUDA_CHECK(cudaMemsetAsync(V, 0, (size_t)m * L.ldv * sizeof(T), st));
+  for (int64_t p = 0; p < L.npanels; ++p) {
+    const int64_t j0 = p * QR_NB;
+    const int jb = (int)((k - j0 < QR_NB) ? (k - j0) : QR_NB);
+    QrPanelArgs a;
+    a.W = W; a.V = V; a.T = Tb + p * QR_NB * QR_NB;
+    a.m = m; a.ldw = L.ldw; a.ldv = L.ldv; a.j0 = j0; a.jb = jb;
+    int rc = launch_panel<T>(a, st);
+    if (rc) return rc;
+    const int64_t n2 = n - j0 - jb, mr = m - j0;
+    if (n2 > 0) {
+      const T* Vp = V + j0 * L.ldv + j0;
+      T* A2 = W + j0 * L.ldw + j0 + jb;
+      // W1 = V^H A2 ; W2 = T^H W1 ; A2 -= V W2
+      rc = gemm(dtype, TNB_OP_C, TNB_OP_N, jb, n2, mr, 1, 0, Vp, L.ldv, 0, A2, L.ldw, 0, 0, 0, W1, n2, 0, 1, st);
+      if (rc) return rc;
+      rc = gemm(dtype, TNB_OP_C, TNB_OP_N, jb, n2, jb, 1, 0, a.T, QR_NB, 0, W1, n2, 0, 0, 0, W2, n2, 0, 1, st);
+      if (rc) return rc;
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, mr, n2, jb, -1, 0, Vp, L.ldv, 0, W2, n2, 0, 1, 0, A2, L.ldw, 0, 1, st);
+      if (rc) return rc;
+    }
+  }
+  if (R) {
+    extract_r_kernel<T><<<blocks_for(k * n), 256, 0, st>>>(W, L.ldw, (T*)R, k, n);
+    TNB_LAUNCH_CHECK();
+  }
+  if (Q) {
+    T* Qo = (T*)Q;
+    eye_kernel<T><<<blocks_for(m * k), 256, 0, st>>>(Qo, m, k, k);
+    TNB_LAUNCH_CHECK();
+    for (int64_t p = L.npanels - 1; p >= 0; --p) {
+      const int64_t j0 = p * QR_NB;
+      const int jb = (int)((k - j0 < QR_NB) ? (k - j0) : QR_NB);
+      const int64_t nc = k - j0, mr = m - j0;
+      const T* Vp = V + j0 * L.ldv + j0;
+      const T* Tp = Tb + p * QR_NB * QR_NB;
+      T* Qs = Qo + j0 * k + j0;
+      // Qs := (I - V T V^H) Qs
+      int rc = gemm(dtype, TNB_OP_C, TNB_OP_N, jb, nc, mr, 1, 0, Vp, L.ldv, 0, Qs, k, 0, 0, 0, W1, nc, 0, 1, st);
+      if (rc) return rc;
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, jb, nc, jb, 1, 0, Tp, QR_NB, 0, W1, nc, 0, 0, 0, W2, nc, 0, 1, st);
+      if (rc) return rc;
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, mr, nc, jb, -1, 0, Vp, L.ldv, 0, W2, nc, 0, 1, 0, Qs, k, 0, 1, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+// internal entry used by svd.cu as well
+int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, cudaStream_t st) {
+  if (dtype == TNB_F64) return qr_impl<double>(dtype, m, n, A, lda, Q, R, ws, st);
+  return qr_impl<cplx>(dtype, m, n, A, lda, Q, R, ws, st);
+}
+size_t qr_workspace(int dtype, int64_t m, int64_t n) { return qr_layout(dtype, m, n).total; }
+
+}  // namespace tnb
+
+extern "C" size_t tnb_qr_workspace(int dtype, int64_t m, int64_t n) {
+  if (m <= 0 || n <= 0 || (dtype != TNB_F64 && dtype != TNB_C128)) return 0;
+  return tnb::qr_workspace(dtype, m, n);
+}
+
+extern "C" int tnb_qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws,
+                      size_t ws_bytes, void* stream) {
+  if (dtype != TNB_F64 && dtype != TNB_C128) return TNB_E_ARG;
+  if (m < 0 || n < 0 || lda < n) return TNB_E_ARG;
+  if (m == 0 || n == 0) return 0;
+  if (!A || !ws) return TNB_E_ARG;
+  if (ws_bytes < tnb::qr_workspace(dtype, m, n)) return TNB_E_WORKSPACE;
+  return tnb::qr(dtype, m, n, A, lda, Q, R, ws, (cudaStream_t)stream);
+}
