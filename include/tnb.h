@@ -137,8 +137,10 @@ int tnb_svd(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
             void* U, double* S, void* Vh, void* ws, size_t ws_bytes, int* sweeps_out, void* stream);
 
 /* ---- truncation rule on device ---------------------------------------------
- * kept = #{ i < (chi>0 ? chi : n) : s[i] > bar }, bar = threshold (absolute)
- * or threshold*s[0] (relative); tensor.py:1137-1152 (chi first, then
+ * kept = #{ i < (chi>0 ? chi : n) : s[i] > bar }, bar = threshold (relative
+ * == 0, absolute) or threshold*s[0] (relative == 1, tensor.py:1150); relative
+ * == 2 tests s[i]/s[0] > threshold instead (the form of onedim_core.py:333-336);
+ * tensor.py:1137-1152 (chi first, then
  * threshold) and onedim_core.py:333-339 (relative to s[0], then chi) give the
  * same count because s is sorted.  info_device[0] = kept (as a double),
  * info_device[1] = s[0], so the host learns both with one 16-byte read;

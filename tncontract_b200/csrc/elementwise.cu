@@ -169,7 +169,9 @@ __global__ void truncation_count_kernel(const double* s, int64_t n, int64_t chi,
   int local = 0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const double v = s[i];
-    if (i < lim && v > bar) local++;
+    // relative == 2: the comparison of onedim_core.py:333-336, s/s0 > threshold, bit for bit
+    const bool above = (relative == 2) ? (v / s0 > threshold) : (v > bar);
+    if (i < lim && above) local++;
     if (s_scaled) s_scaled[i] = v / s0;
   }
   atomicAdd(&cnt, local);

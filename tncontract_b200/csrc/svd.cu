@@ -1,0 +1,548 @@
+// Thin SVD (np.linalg.svd(full_matrices=False), reference call site
+// tensor.py:915) for float64 / complex128, entirely on the device.
+//
+//   A (m x n)  ->  U (m x k), S (k, descending), Vh (k x n),  k = min(m, n)
+//
+// Algorithm (no Gram-matrix shortcut on A itself -- that would square the
+// condition number and lose the small singular values):
+//   1. QR pre-reduction to a k x k triangular factor (qr.cu): A = Q R when
+//      m >= n, A^H = Q R otherwise.
+//   2. One-sided (Hestenes) block Jacobi on X = R^H:  X V = Y with mutually
+//      orthogonal columns, so R^H = Y V^H.  Working on R^H rather than R is the
+//      Drmac-Veselic preconditioning: its columns are much closer to
+//      orthogonal and the sweep count drops.
+//   3. sigma_j = |Y[:, j]|, sorted on the device; U / Vh assembled with one
+//      DMMA GEMM (Q V) and one gather/scale kernel (Y / sigma).
+//
+// Jacobi layout: the "columns" being orthogonalised are stored as ROWS of
+// Xt (k x k) and Vt (k x k, starts as I), so a column is contiguous.  Columns
+// are grouped in blocks of JB = 16.  One sweep is a round-robin tournament
+// over block pairs (nblk - 1 rounds, nblk/2 independent pairs per round); one
+// kernel launch per round.  A pair is handled by one thread-block CLUSTER:
+//   * the 32 rows of the pair (both Xt and Vt, viewed as one long row) are cut
+//     into chunks of CH elements; each CTA of the cluster owns chunks
+//     crank, crank+S, ... and keeps the last Xt chunk it read resident in
+//     shared memory;
+//   * each CTA forms the partial 32 x 32 Gram matrix of its Xt chunks, the
+//     partials are summed through distributed shared memory (two cluster
+//     barriers, identical summation order everywhere, so every CTA holds the
+//     same bits);
+//   * every CTA runs the same parallel-ordered two-sided Jacobi sweep on the
+//     Gram matrix in shared memory (31 steps of 16 disjoint rotations,
+//     thread (a, b) owns the 2 x 2 block between rotation pairs a and b), which
+//     yields the 32 x 32 unitary W of accumulated rotations; the rotation
+//     angles are exactly those of one-sided Jacobi on the columns;
+//   * every CTA applies W to its chunks (rows_new = W^T rows) and stores them.
+// Convergence: the largest |x_p^H x_q| / (|x_p||x_q|) seen before rotating is
+// accumulated with atomicMax; a one-thread kernel closes each sweep and sets a
+// device flag that turns the remaining queued launches into no-ops, so the
+// host only synchronises every few sweeps.  tol = sqrt(k) * eps (as LAPACK's
+// xGESVJ).  HBM/L2 traffic per round: Xt and Vt read once and written once.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tnb {
+
+int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
+         int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
+         int64_t sC, int64_t batch, cudaStream_t st);
+int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, cudaStream_t st);
+size_t qr_workspace(int dtype, int64_t m, int64_t n);
+int permute_view(int dtype, const void* in, int rank, const int64_t* oshape, const int64_t* istride, void* out,
+                 double ar, double ai, int conj, cudaStream_t st);
+
+constexpr int JB = 16;       // Jacobi block width (columns)
+constexpr int JP = 2 * JB;   // columns in a block pair
+constexpr int JT = 256;      // threads per CTA = (JP/2)^2: thread (a, b) owns a 2x2 block
+constexpr int JGP = JP + 1;  // pitch of the small matrices in shared memory
+constexpr int MAX_SWEEPS = 60;
+
+struct JacobiFlags {
+  unsigned long long maxoff_bits;  // max off-diagonal cosine of the sweep in flight (double bits)
+  int converged;
+  int sweeps;  // completed sweeps (stops counting once converged)
+};
+
+struct JacobiArgs {
+  void* X;
+  void* V;
+  int64_t n;    // number of Jacobi columns (= rows of Xt, Vt, and row length of Vt)
+  int64_t L;    // row length of Xt
+  int64_t ldx, ldv;
+  int nblk;     // even number of column blocks (the last ones may be empty)
+  int round;
+  int S;        // CTAs per cluster
+  int CH;       // chunk length (power of two)
+  int nx, nv;   // chunks per Xt row / per Vt row
+  double tol;
+  JacobiFlags* flags;
+};
+
+// round-robin tournament (circle method), n even: pair p of round r
+__host__ __device__ __forceinline__ void rr_pair(int n, int r, int p, int& a, int& b) {
+  if (p == 0) { a = n - 1; b = r; return; }
+  a = (r + p) % (n - 1);
+  b = (r - p + n - 1) % (n - 1);
+}
+
+template <typename T> __device__ __forceinline__ double abs_t(T v);
+template <> __device__ __forceinline__ double abs_t<double>(double v) { return fabs(v); }
+template <> __device__ __forceinline__ double abs_t<cplx>(cplx v) { return hypot(v.x, v.y); }
+
+// Rotation J = [[c, sp], [-conj(sp), c]] acting on columns (x_p, x_q) -> (x_p, x_q) J that
+// annihilates x_p^H x_q; identity when the pair is already orthogonal to `tol`.
+template <typename T> struct Rot { double c; T sp; double off; };
+
+template <typename T>
+__device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol) {
+  typedef Num<T> N_;
+  Rot<T> r;
+  r.c = 1.0; r.sp = N_::zero(); r.off = 0.0;
+  const double alpha = N_::real(G[p * JGP + p]), beta = N_::real(G[q * JGP + q]);
+  const T gam = G[p * JGP + q];
+  const double ag = abs_t<T>(gam);
+  if (alpha > 0.0 && beta > 0.0 && ag > 0.0) {
+    const double den = sqrt(alpha) * sqrt(beta);
+    if (den > 0.0) {
+      r.off = ag / den;
+      if (r.off > tol) {
+        const double zeta = (beta - alpha) / (2.0 * ag);
+        double t;
+        if (fabs(zeta) > 1e100) t = 0.5 / zeta;
+        else t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        r.c = 1.0 / sqrt(1.0 + t * t);
+        const double s = r.c * t;
+        r.sp = N_::scale(gam, s / ag);
+      }
+    }
+  }
+  return r;
+}
+
+// Shared memory: P[JP][CH+1] | G[JP][JGP] | Gpart[JP][JGP] | W[JP][JGP]
+template <typename T>
+__global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
+  typedef Num<T> N_;
+  if (a.flags->converged) return;  // uniform over the whole grid
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = a.S;
+  const int crank = (int)cluster.block_rank();
+  const int pair = blockIdx.x / S;
+  int bI, bJ;
+  rr_pair(a.nblk, a.round, pair, bI, bJ);
+  if (bI > bJ) { const int t = bI; bI = bJ; bJ = t; }
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int CH = a.CH, pitch = CH + 1;
+  T* P = reinterpret_cast<T*>(smem_raw);
+  T* G = P + (size_t)JP * pitch;
+  T* Gpart = G + JP * JGP;
+  T* W = Gpart + JP * JGP;
+
+  const int tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
+  T* Xg = reinterpret_cast<T*>(a.X);
+  T* Vg = reinterpret_cast<T*>(a.V);
+
+  auto grow = [&](int i) -> int64_t {  // global row of panel row i, or -1
+    const int64_t r = (i < JB) ? ((int64_t)bI * JB + i) : ((int64_t)bJ * JB + (i - JB));
+    return (r < a.n) ? r : (int64_t)-1;
+  };
+  auto chunk_geom = [&](int g, T*& base, int64_t& ld, int64_t& c0, int& len) {
+    if (g < a.nx) { base = Xg; ld = a.ldx; c0 = (int64_t)g * CH; const int64_t rem = a.L - c0; len = (int)(rem < CH ? rem : CH); }
+    else { base = Vg; ld = a.ldv; c0 = (int64_t)(g - a.nx) * CH; const int64_t rem = a.n - c0; len = (int)(rem < CH ? rem : CH); }
+  };
+  auto load_chunk = [&](int g) {
+    T* base; int64_t ld, c0; int len;
+    chunk_geom(g, base, ld, c0, len);
+    for (int idx = tid; idx < JP * CH; idx += JT) {
+      const int i = idx / CH, c = idx - i * CH;
+      const int64_t r = grow(i);
+      T v = N_::zero();
+      if (r >= 0 && c < len) v = base[r * ld + c0 + c];
+      P[i * pitch + c] = v;
+    }
+  };
+
+  // ---- partial Gram matrix of this CTA's Xt chunks -----------------------------------
+  T acc[2][2];
+  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = N_::zero();
+  int resident = -1;
+  for (int g = crank; g < a.nx; g += S) {
+    __syncthreads();
+    load_chunk(g);
+    __syncthreads();
+    resident = g;
+    const T* ra0 = P + (2 * ta) * pitch;
+    const T* ra1 = ra0 + pitch;
+    const T* rb0 = P + (2 * tb) * pitch;
+    const T* rb1 = rb0 + pitch;
+#pragma unroll 4
+    for (int c = 0; c < CH; ++c) {
+      const T x0 = ra0[c], x1 = ra1[c], y0 = rb0[c], y1 = rb1[c];
+      acc[0][0] = N_::fma_conj(x0, y0, acc[0][0]);
+      acc[0][1] = N_::fma_conj(x0, y1, acc[0][1]);
+      acc[1][0] = N_::fma_conj(x1, y0, acc[1][0]);
+      acc[1][1] = N_::fma_conj(x1, y1, acc[1][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) Gpart[(2 * ta + i) * JGP + 2 * tb + j] = acc[i][j];
+  for (int idx = tid; idx < JP * JP; idx += JT) {
+    const int i = idx / JP, j = idx - i * JP;
+    W[i * JGP + j] = (i == j) ? N_::one() : N_::zero();
+  }
+  cluster.sync();
+  for (int idx = tid; idx < JP * JP; idx += JT) {
+    const int i = idx / JP, j = idx - i * JP;
+    T s = N_::zero();
+    for (int q = 0; q < S; ++q) s = N_::add(s, cluster.map_shared_rank(Gpart, q)[i * JGP + j]);
+    G[i * JGP + j] = s;
+  }
+  cluster.sync();  // all remote reads done before any CTA moves on (or exits)
+
+  // ---- one parallel-ordered Jacobi sweep on G, rotations accumulated in W ------------
+  double maxoff = 0.0;
+  for (int step = 0; step < JP - 1; ++step) {
+    int pa, qa, pb, qb;
+    rr_pair(JP, step, ta, pa, qa);
+    rr_pair(JP, step, tb, pb, qb);
+    if (pa > qa) { const int t = pa; pa = qa; qa = t; }
+    if (pb > qb) { const int t = pb; pb = qb; qb = t; }
+    const Rot<T> Ra = make_rot<T>(G, pa, qa, a.tol);
+    const Rot<T> Rb = make_rot<T>(G, pb, qb, a.tol);
+    const T b00 = G[pa * JGP + pb], b01 = G[pa * JGP + qb], b10 = G[qa * JGP + pb], b11 = G[qa * JGP + qb];
+    const T w00 = W[(2 * ta) * JGP + pb], w01 = W[(2 * ta) * JGP + qb];
+    const T w10 = W[(2 * ta + 1) * JGP + pb], w11 = W[(2 * ta + 1) * JGP + qb];
+    __syncthreads();
+    // T1 = B J_b
+    const T csb = N_::conj(Rb.sp);
+    const T t00 = N_::sub(N_::scale(b00, Rb.c), N_::mul(csb, b01));
+    const T t01 = N_::add(N_::mul(Rb.sp, b00), N_::scale(b01, Rb.c));
+    const T t10 = N_::sub(N_::scale(b10, Rb.c), N_::mul(csb, b11));
+    const T t11 = N_::add(N_::mul(Rb.sp, b10), N_::scale(b11, Rb.c));
+    // B' = J_a^H T1,  J_a^H = [[c, -sp], [conj(sp), c]]
+    const T csa = N_::conj(Ra.sp);
+    T n00 = N_::sub(N_::scale(t00, Ra.c), N_::mul(Ra.sp, t10));
+    T n01 = N_::sub(N_::scale(t01, Ra.c), N_::mul(Ra.sp, t11));
+    T n10 = N_::add(N_::mul(csa, t00), N_::scale(t10, Ra.c));
+    T n11 = N_::add(N_::mul(csa, t01), N_::scale(t11, Ra.c));
+    if (ta == tb) {
+      // diagonal block: real diagonal, exact zero where a rotation was applied
+      n00 = N_::from(N_::real(n00), 0.0);
+      n11 = N_::from(N_::real(n11), 0.0);
+      if (Ra.c != 1.0 || N_::abs2(Ra.sp) != 0.0) { n01 = N_::zero(); n10 = N_::zero(); }
+      if (Ra.off > maxoff) maxoff = Ra.off;
+    }
+    G[pa * JGP + pb] = n00; G[pa * JGP + qb] = n01; G[qa * JGP + pb] = n10; G[qa * JGP + qb] = n11;
+    // W' = W J_b on rows 2ta, 2ta+1
+    W[(2 * ta) * JGP + pb] = N_::sub(N_::scale(w00, Rb.c), N_::mul(csb, w01));
+    W[(2 * ta) * JGP + qb] = N_::add(N_::mul(Rb.sp, w00), N_::scale(w01, Rb.c));
+    W[(2 * ta + 1) * JGP + pb] = N_::sub(N_::scale(w10, Rb.c), N_::mul(csb, w11));
+    W[(2 * ta + 1) * JGP + qb] = N_::add(N_::mul(Rb.sp, w10), N_::scale(w11, Rb.c));
+    __syncthreads();
+  }
+  if (crank == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, maxoff, o);
+      if (other > maxoff) maxoff = other;
+    }
+    if ((tid & 31) == 0 && maxoff > 0.0)
+      atomicMax(&a.flags->maxoff_bits, (unsigned long long)__double_as_longlong(maxoff));
+  }
+
+  // ---- rows_new[q] = sum_p W[p][q] rows[p] on every chunk of this CTA --------------------
+  auto apply_chunk = [&](int g) {
+    T* base; int64_t ld, c0; int len;
+    chunk_geom(g, base, ld, c0, len);
+    for (int c = tid; c < len; c += JT) {
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        T out[JB];
+#pragma unroll
+        for (int q = 0; q < JB; ++q) out[q] = N_::zero();
+#pragma unroll 2
+        for (int p = 0; p < JP; ++p) {
+          const T x = P[p * pitch + c];
+          const T* wrow = W + p * JGP + half * JB;
+#pragma unroll
+          for (int q = 0; q < JB; ++q) out[q] = N_::fma(wrow[q], x, out[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < JB; ++q) {
+          const int64_t r = grow(half * JB + q);
+          if (r >= 0) base[r * ld + c0 + c] = out[q];
+        }
+      }
+    }
+  };
+  if (resident >= 0) apply_chunk(resident);
+  for (int g = crank; g < a.nx + a.nv; g += S) {
+    if (g == resident) continue;
+    __syncthreads();
+    load_chunk(g);
+    __syncthreads();
+    apply_chunk(g);
+  }
+}
+
+__global__ void jacobi_finish_sweep_kernel(JacobiFlags* f, double tol) {
+  if (f->converged) return;
+  const double off = __longlong_as_double((long long)f->maxoff_bits);
+  f->sweeps += 1;
+  if (off <= tol) f->converged = 1;
+  f->maxoff_bits = 0ull;
+}
+
+// sigma[j] = |Xt[j, :]|, one warp per row (scaled two-pass-free: values are O(|A|), no overflow risk
+// beyond that of the input's own Frobenius norm)
+template <typename T>
+__global__ void __launch_bounds__(256) row_norm_kernel(const T* X, int64_t ld, int64_t n, int64_t L, double* sigma) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  for (int64_t c = lane; c < L; c += 32) acc += Num<T>::abs2(X[row * ld + c]);
+  acc = warp_sum(acc);
+  if (lane == 0) sigma[row] = sqrt(acc);
+}
+
+// descending rank by counting (stable): perm[rank] = j, S[rank] = sigma[j]
+__global__ void __launch_bounds__(256) rank_kernel(const double* sigma, int64_t n, int32_t* perm, double* S) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double sj = sigma[j];
+  int64_t r = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double si = sigma[i];
+    r += (si > sj || (si == sj && i < j)) ? 1 : 0;
+  }
+  perm[r] = (int32_t)j;
+  S[r] = sj;
+}
+
+// out[k, c] = f(in[perm[k], c])            (transpose == 0, out ld = ldo)
+// out[c, k] = f(in[perm[k], c])            (transpose == 1)
+// f: optional conjugation and division by S[k] (zero singular value -> zero vector)
+template <typename T>
+__global__ void gather_rows_kernel(const T* in, int64_t ldi, const int32_t* perm, const double* S, T* out, int64_t ldo,
+                                   int64_t n, int64_t L, int conj, int scale, int transpose) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * L; i += step) {
+    int64_t k, c;
+    if (transpose) { c = i / n; k = i - c * n; } else { k = i / L; c = i - k * L; }
+    T v = in[(int64_t)perm[k] * ldi + c];
+    if (conj) v = Num<T>::conj(v);
+    if (scale) { const double s = S[k]; v = Num<T>::scale(v, s > 0.0 ? 1.0 / s : 0.0); }
+    if (transpose) out[c * ldo + k] = v; else out[k * ldo + c] = v;
+  }
+}
+
+template <typename T>
+__global__ void eye_rows_kernel(T* V, int64_t n) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * n; i += step) {
+    const int64_t r = i / n, c = i - r * n;
+    V[i] = (r == c) ? Num<T>::one() : Num<T>::zero();
+  }
+}
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline unsigned blocks_for(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+struct SvdLayout {
+  int64_t k, mq, nq;  // QR problem: mq x nq with nq == k
+  size_t off_ah, off_q, off_r, off_x, off_v, off_vs, off_sig, off_perm, off_flags, off_qr, total;
+};
+
+static SvdLayout svd_layout(int dtype, int64_t m, int64_t n) {
+  SvdLayout L;
+  const size_t es = elem_size(dtype);
+  L.k = m < n ? m : n;
+  L.mq = m < n ? n : m;
+  L.nq = L.k;
+  size_t o = 0;
+  L.off_ah = o;    o += (m < n) ? align_up((size_t)m * n * es) : 0;
+  L.off_q = o;     o += align_up((size_t)L.mq * L.k * es);
+  L.off_r = o;     o += align_up((size_t)L.k * L.k * es);
+  L.off_x = o;     o += align_up((size_t)L.k * L.k * es);
+  L.off_v = o;     o += align_up((size_t)L.k * L.k * es);
+  L.off_vs = o;    o += align_up((size_t)L.k * L.k * es);
+  L.off_sig = o;   o += align_up((size_t)L.k * sizeof(double));
+  L.off_perm = o;  o += align_up((size_t)L.k * sizeof(int32_t));
+  L.off_flags = o; o += align_up(sizeof(JacobiFlags));
+  L.off_qr = o;    o += align_up(qr_workspace(dtype, L.mq, L.nq));
+  L.total = o;
+  return L;
+}
+
+template <typename T>
+static int launch_round(JacobiArgs& a, int npairs, size_t smem, cudaStream_t st) {
+  auto kern = jacobi_round_kernel<T>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(npairs * a.S), 1, 1);
+  cfg.blockDim = dim3(JT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)a.S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+  ++g_launches;
+  return 0;
+}
+
+// Orthogonalise the rows-as-columns of Xt (n x L) in place, accumulating V in Vt (n x n, must be I).
+template <typename T>
+static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* flags, int* sweeps_out,
+                  cudaStream_t st) {
+  const bool cplx = sizeof(T) == 16;
+  const int64_t nblk_real = (n + JB - 1) / JB;
+  int nblk = (int)(nblk_real + (nblk_real & 1));
+  if (nblk < 2) nblk = 2;
+  const int npairs = nblk / 2, rounds = nblk - 1;
+  JacobiArgs a;
+  a.X = Xt; a.V = Vt; a.n = n; a.L = L; a.ldx = ldx; a.ldv = n; a.nblk = nblk; a.flags = flags;
+  a.tol = sqrt((double)(L > 1 ? L : 1)) * 2.220446049250313e-16;
+  const int ch_max = cplx ? 256 : 512;
+  int CH = 32;
+  const int64_t longest = L > n ? L : n;
+  while (CH < ch_max && CH < longest) CH *= 2;
+  a.CH = CH;
+  a.nx = (int)((L + CH - 1) / CH);
+  a.nv = (int)((n + CH - 1) / CH);
+  int S = 1;
+  while (S * 2 <= 8 && S * 2 <= a.nx + a.nv && npairs * S * 2 <= sm_count()) S *= 2;
+  a.S = S;
+  const size_t smem = ((size_t)JP * (CH + 1) + 3 * (size_t)JP * JGP) * sizeof(T);
+  TNB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(JacobiFlags), st));
+  int queued = 0;
+  JacobiFlags h;
+  h.converged = 0; h.sweeps = 0; h.maxoff_bits = 0;
+  while (queued < MAX_SWEEPS) {
+    const int batch = (queued == 0) ? 5 : 2;
+    for (int s = 0; s < batch; ++s) {
+      for (int r = 0; r < rounds; ++r) {
+        a.round = r;
+        int rc = launch_round<T>(a, npairs, smem, st);
+        if (rc) return rc;
+      }
+      jacobi_finish_sweep_kernel<<<1, 1, 0, st>>>(flags, a.tol);
+      TNB_LAUNCH_CHECK();
+    }
+    queued += batch;
+    TNB_CUDA_CHECK(cudaMemcpyAsync(&h, flags, sizeof(JacobiFlags), cudaMemcpyDeviceToHost, st));
+    TNB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h.converged) break;
+  }
+  if (sweeps_out) *sweeps_out = h.sweeps;
+  return h.converged ? 0 : TNB_E_NOCONV;
+}
+
+template <typename T>
+static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* U, double* S, void* Vh,
+                    void* ws, int* sweeps_out, cudaStream_t st) {
+  const SvdLayout L = svd_layout(dtype, m, n);
+  char* base = (char*)ws;
+  const int64_t k = L.k;
+  T* Q = (T*)(base + L.off_q);
+  T* R = (T*)(base + L.off_r);
+  T* Xt = (T*)(base + L.off_x);
+  T* Vt = (T*)(base + L.off_v);
+  T* Vs = (T*)(base + L.off_vs);
+  double* sig = (double*)(base + L.off_sig);
+  int32_t* perm = (int32_t*)(base + L.off_perm);
+  JacobiFlags* flags = (JacobiFlags*)(base + L.off_flags);
+  void* qr_ws = base + L.off_qr;
+  const bool wide = m < n;
+  int rc;
+  if (!wide) {
+    rc = qr(dtype, m, n, A, lda, Q, R, qr_ws, st);
+    if (rc) return rc;
+  } else {
+    T* AH = (T*)(base + L.off_ah);  // A^H, n x m contiguous
+    const int64_t sh[2] = {n, m}, is[2] = {1, lda};
+    rc = permute_view(dtype, A, 2, sh, is, AH, 1.0, 0.0, 1, st);
+    if (rc) return rc;
+    rc = qr(dtype, n, m, AH, m, Q, R, qr_ws, st);
+    if (rc) return rc;
+  }
+  {  // Xt = conj(R): row j of Xt is column j of X = R^H
+    const int64_t sh[2] = {k, k}, is[2] = {k, 1};
+    rc = permute_view(dtype, R, 2, sh, is, Xt, 1.0, 0.0, 1, st);
+    if (rc) return rc;
+  }
+  eye_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Vt, k);
+  TNB_LAUNCH_CHECK();
+  rc = jacobi<T>(Xt, k, k, Vt, k, flags, sweeps_out, st);
+  if (rc) return rc;
+  row_norm_kernel<T><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(Xt, k, k, k, sig);
+  TNB_LAUNCH_CHECK();
+  rank_kernel<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(sig, k, perm, S);
+  TNB_LAUNCH_CHECK();
+  // Vs[j, :] = Vt[perm[j], :]  (column j of the sorted V, as a row)
+  gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Vt, k, perm, S, Vs, k, k, k, 0, 0, 0);
+  TNB_LAUNCH_CHECK();
+  if (!wide) {
+    // A = Q R, R = V Sigma Ux^H:  U = Q V,  Vh = Ux^H = conj(Y^T) / sigma
+    if (Vh) {
+      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, S, (T*)Vh, n, k, k, 1, 1, 0);
+      TNB_LAUNCH_CHECK();
+    }
+    if (U) {
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_T, m, k, k, 1, 0, Q, k, 0, Vs, k, 0, 0, 0, U, k, 0, 1, st);
+      if (rc) return rc;
+    }
+  } else {
+    // A = R^H Q^H = Ux Sigma (Q V)^H:  U = Y / sigma,  Vh = conj(Vs) Q^H
+    if (U) {
+      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, S, (T*)U, k, k, k, 0, 1, 1);
+      TNB_LAUNCH_CHECK();
+    }
+    if (Vh) {
+      rc = gemm(dtype, TNB_OP_J, TNB_OP_C, k, n, k, 1, 0, Vs, k, 0, Q, k, 0, 0, 0, Vh, n, 0, 1, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+}  // namespace tnb
+
+extern "C" size_t tnb_svd_workspace(int dtype, int64_t m, int64_t n) {
+  if (m <= 0 || n <= 0 || (dtype != TNB_F64 && dtype != TNB_C128)) return 0;
+  return tnb::svd_layout(dtype, m, n).total;
+}
+
+extern "C" int tnb_svd(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* U, double* S, void* Vh,
+                       void* ws, size_t ws_bytes, int* sweeps_out, void* stream) {
+  if (dtype != TNB_F64 && dtype != TNB_C128) return TNB_E_ARG;
+  if (m < 0 || n < 0 || lda < n) return TNB_E_ARG;
+  if (sweeps_out) *sweeps_out = 0;
+  if (m == 0 || n == 0) return 0;
+  if (!A || !S || !ws) return TNB_E_ARG;
+  if (ws_bytes < tnb::svd_layout(dtype, m, n).total) return TNB_E_WORKSPACE;
+  if (dtype == TNB_F64) return tnb::svd_impl<double>(dtype, m, n, A, lda, U, S, Vh, ws, sweeps_out, (cudaStream_t)stream);
+  return tnb::svd_impl<tnb::cplx>(dtype, m, n, A, lda, U, S, Vh, ws, sweeps_out, (cudaStream_t)stream);
+}

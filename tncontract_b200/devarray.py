@@ -71,7 +71,7 @@ class DevArray:
     def from_host(obj):
         a = _canon_dtype(np.asarray(obj))
         _require_cuda()
-        t = torch.from_numpy(np.ascontiguousarray(a)).to(device())
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device(), copy=True)  # always a private copy
         return DevArray(t.reshape(a.shape))
 
     @staticmethod
