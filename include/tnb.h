@@ -58,6 +58,14 @@ int tnb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of libtnb kernels launched by this process so far (reset != 0 zeroes it) */
 long long tnb_launch_count(int reset);
 
+/* Optional device-time profile by kernel class (CUDA events on the launching
+ * stream; bench.py uses it for the roofline figures).  enable(1) clears and
+ * starts, enable(0) stops.  classes: 0 gemm (work = flops), 1 jacobi rounds
+ * (flops executed), 2 qr panel (flops), 3 permute (bytes), 4 mps_mpo_site
+ * (bytes), 5 elementwise (bytes).  get() synchronises on the recorded events. */
+int tnb_profile_enable(int on);
+int tnb_profile_get(int cls, double* ms, double* work, long long* launches, long long* scopes);
+
 /* ---- index permutation: np.rollaxis/np.transpose + np.reshape copy -------
  * replaces the materialised copies behind tensor.py:295,315,354,363,392-394,
  * 482,818,911,1041 and ndarray.copy()/conjugate() (tensor.py:378,485).

@@ -24,3 +24,25 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def _cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        return False
+
+
+@pytest.fixture(params=["host", pytest.param("gpu", marks=pytest.mark.gpu)])
+def backend(request, monkeypatch):
+    """"host": the Python layer of tncontract_b200 over tests/fake_tnb.py (NumPy
+    stand-in of the C ABI, checks label algebra / sweep logic on CPU);
+    "gpu": the real libtnb.so on cuda:0 (the parity tests proper)."""
+    if request.param == "host":
+        import fake_tnb
+        fake_tnb.install(monkeypatch)
+    else:
+        if not _cuda():
+            pytest.skip("no CUDA device")
+    return request.param

@@ -39,6 +39,8 @@ SIGNATURES = {
     "tnb_error_string": (_c.c_char_p, [_c.c_int]),
     "tnb_device_info": (_c.c_int, [_pi32, _pi32, _pi32]),
     "tnb_launch_count": (_c.c_longlong, [_c.c_int]),
+    "tnb_profile_enable": (_c.c_int, [_c.c_int]),
+    "tnb_profile_get": (_c.c_int, [_c.c_int, _pdbl, _pdbl, _c.POINTER(_c.c_longlong), _c.POINTER(_c.c_longlong)]),
     "tnb_permute": (_c.c_int, [_pd, _pi32, _vp, _dbl, _dbl, _c.c_int, _vp]),
     "tnb_scale_inplace": (_c.c_int, [_pd, _dbl, _dbl, _vp]),
     "tnb_axpby": (_c.c_int, [_pd, _pd, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),

@@ -23,6 +23,20 @@ namespace tnb { extern long long g_launches; }
 
 namespace tnb {
 
+// kernel classes of the optional device-time profile (prof.cu, tnb_profile_*)
+enum { KC_GEMM = 0, KC_JACOBI = 1, KC_QR_PANEL = 2, KC_PERMUTE = 3, KC_MPO_APPLY = 4, KC_ELEMWISE = 5, KC_COUNT = 6 };
+extern bool g_prof_on;
+// RAII: brackets the kernel launches made during its lifetime with two CUDA
+// events on `st` when profiling is on; `work` = algorithmic flops or bytes.
+struct ProfScope {
+  int cls;
+  cudaStream_t st;
+  double work;
+  long long l0, idx;
+  ProfScope(int c, cudaStream_t s, double w);
+  ~ProfScope();
+};
+
 typedef double2 cplx;  // interleaved complex128
 
 __host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
