@@ -192,6 +192,11 @@ def test_qr(cplx):
         # R is unique up to the signs of its rows: compare |diag| with LAPACK
         rr = np.linalg.qr(a, mode="r")
         assert rel(np.abs(np.diag(r)), np.abs(np.diag(rr))) < TOL, (m, n)
+    # magnitudes whose squares overflow / underflow (LAPACK's scaled norms survive these)
+    for scale in (1e170, 1e-170):
+        a = rnd(rng, (30, 10), cplx) * scale
+        q, r = dv.qr(dv.DevArray.from_host(a))
+        assert rel(np.asarray(q) @ np.asarray(r), a) < TOL
     # rank-deficient and zero columns must not produce NaNs
     a = rnd(rng, (30, 10), cplx)
     a[:, 3] = 0
@@ -253,6 +258,16 @@ def test_svd_hard_spectra(cplx):
     c = rng.random((128, 64)) + (1j * rng.random((128, 64)) if cplx else 0)
     u, s, vh = dv.svd(dv.DevArray.from_host(c))
     _check_svd(c, np.asarray(u), np.asarray(s), np.asarray(vh))
+    # huge / tiny magnitudes: the Gram matrices inside Jacobi must not overflow or underflow
+    for scale in (1e170, 1e-170):
+        e = rnd(rng, (40, 24), cplx)
+        u, s, vh = dv.svd(dv.DevArray.from_host(e * scale))
+        _check_svd(e, np.asarray(u), np.asarray(s) / scale, np.asarray(vh))
+    # NaN input -> LinAlgError, like numpy.linalg.svd
+    e = rnd(rng, (12, 9), cplx)
+    e[3, 4] = np.nan
+    with pytest.raises(np.linalg.LinAlgError):
+        dv.svd(dv.DevArray.from_host(e))
     # zero matrix
     z = np.zeros((8, 5), dtype=complex if cplx else float)
     u, s, vh = dv.svd(dv.DevArray.from_host(z))

@@ -72,7 +72,7 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise TnbError("libtnb.so not found at %s -- run `python -m tncontract_b200.build` "
+        raise TnbError("libtnb.so not found at %s -- run `python tncontract_b200/build.py` "
                        "(there is no CPU fallback)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

@@ -1,6 +1,8 @@
 """Build libtnb.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
 
-    python -m tncontract_b200.build [--force]
+    python tncontract_b200/build.py [--force] [-v]
+
+(run by path: importing the package needs the library this script produces)
 
 The library is compiled for sm_100a only (-gencode arch=compute_100a,
 code=sm_100a) and linked with the static CUDA runtime, so the .so travels to

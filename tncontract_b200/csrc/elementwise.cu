@@ -189,6 +189,7 @@ extern "C" int tnb_scale_inplace(const tnb_tensor_t* x, double ar, double ai, vo
   ViewParams p = make_view(x);
   if (p.numel == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(KC_ELEMWISE, st, 2.0 * (double)p.numel * (double)elem_size(x->dtype));
   if (x->dtype == TNB_F64) scale_inplace_kernel<double><<<grid_for(p.numel), 256, 0, st>>>((double*)x->ptr, p, ar, ai);
   else scale_inplace_kernel<double2><<<grid_for(p.numel), 256, 0, st>>>((double2*)x->ptr, p, ar, ai);
   TNB_LAUNCH_CHECK();
@@ -237,6 +238,7 @@ extern "C" int tnb_norm2(const tnb_tensor_t* x, double* out_device, void* ws, si
   if (blocks > NORM_BLOCKS) blocks = NORM_BLOCKS;
   if (blocks < 1) blocks = 1;
   TNB_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+  ProfScope prof(KC_ELEMWISE, st, (double)p.numel * (double)elem_size(x->dtype));
   if (x->dtype == TNB_F64)
     norm2_kernel<double><<<(unsigned)blocks, NORM_THREADS, 0, st>>>((const double*)x->ptr, p, out_device, partial, ticket);
   else
@@ -275,6 +277,7 @@ extern "C" int tnb_diag_scale(int dtype, void* x, int64_t rows, int64_t cols, in
   if (!x || !s || rows < 0 || cols < 0 || ld < cols || (axis != 0 && axis != 1) || mode < 0 || mode > 2) return TNB_E_ARG;
   if (rows * cols == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(KC_ELEMWISE, st, 2.0 * (double)rows * (double)cols * (double)elem_size(dtype));
   if (dtype == TNB_F64) diag_scale_kernel<double><<<grid_for(rows * cols), 256, 0, st>>>((double*)x, rows, cols, ld, s, axis, mode);
   else if (dtype == TNB_C128) diag_scale_kernel<double2><<<grid_for(rows * cols), 256, 0, st>>>((double2*)x, rows, cols, ld, s, axis, mode);
   else return TNB_E_ARG;

@@ -294,6 +294,7 @@ int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar
     return 0;
   }
   if (!A || !B) return TNB_E_ARG;
+  ProfScope prof(KC_GEMM, st, (cplx ? 8.0 : 2.0) * (double)M * (double)N * (double)K * (double)batch);
   GemmArgs g;
   g.A = A; g.B = B; g.C = C;
   g.M = M; g.N = N; g.K = K;

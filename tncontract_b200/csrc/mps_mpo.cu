@@ -76,6 +76,8 @@ extern "C" int tnb_mps_mpo_site(const tnb_tensor_t* A, const tnb_tensor_t* W, vo
   if (gy > 65535) gy = 65535;
   dim3 grid((unsigned)rows, (unsigned)gy);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(KC_MPO_APPLY, st, (double)elem_size(A->dtype) *
+                                       ((double)rows * ncol + (double)numel(A) + (double)numel(W)));
   if (A->dtype == TNB_F64)
     mps_mpo_site_kernel<double><<<grid, 256, smem, st>>>((const double*)A->ptr, (const double*)W->ptr, (double*)out, p);
   else

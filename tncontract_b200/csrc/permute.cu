@@ -175,6 +175,7 @@ int permute_view(int dtype, const void* in, int rank, const int64_t* oshape, con
   p.ar = ar; p.ai = ai;
   p.conj = (dtype == TNB_C128) ? (conj != 0) : 0;
   p.scale = !(ar == 1.0 && ai == 0.0);
+  ProfScope prof(KC_PERMUTE, st, 2.0 * (double)v.numel * (double)elem_size(dtype));
   if (dtype == TNB_C128) return launch_permute<1>(in, out, p, st);
   // float64: move pairs as 16-byte packets when the inner run allows it
   const int last = p.rank - 1;

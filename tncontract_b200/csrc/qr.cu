@@ -229,22 +229,52 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
   }
 }
 
-// copy A (lda) -> W (ldw), contiguous rows
+// max |re|, |im| over a matrix -> atomicMax on the bit pattern (non-negative doubles order like integers)
 template <typename T>
-__global__ void copy2d_kernel(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows, int64_t cols) {
+__global__ void amax_kernel(const T* src, int64_t lds, int64_t rows, int64_t cols, unsigned long long* out) {
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  double m = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += step) {
     const int64_t r = i / cols, c = i - r * cols;
-    dst[r * ldd + c] = src[r * lds + c];
+    const T v = src[r * lds + c];
+    double a;
+    if constexpr (sizeof(T) == 16) a = fmax(fabs(v.x), fabs(v.y)); else a = fabs(v);
+    if (a > m) m = a;  // NaN never wins; it propagates through the factorisation itself
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, m, o);
+    if (other > m) m = other;
+  }
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+// scale[0] = 2^-ilogb(amax) (exact power of two: scaling by it is rounding-free), 1 for zero / non-finite
+__global__ void pow2_scale_kernel(const unsigned long long* amax_bits, double* scale) {
+  const double a = __longlong_as_double((long long)amax_bits[0]);
+  double s = 1.0;
+  if (a > 0.0 && isfinite(a)) s = scalbn(1.0, -ilogb(a));
+  scale[0] = s;
+  scale[1] = 1.0 / s;
+}
+// copy A (lda) -> W (ldw), contiguous rows, times scale[0] when given
+template <typename T>
+__global__ void copy2d_kernel(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows, int64_t cols,
+                              const double* scale) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const double s = scale ? scale[0] : 1.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += step) {
+    const int64_t r = i / cols, c = i - r * cols;
+    dst[r * ldd + c] = Num<T>::scale(src[r * lds + c], s);
   }
 }
-// R = triu(W[0:k, 0:n])
+// R = triu(W[0:k, 0:n]) (times unscale[1] when given)
 template <typename T>
-__global__ void extract_r_kernel(const T* W, int64_t ldw, T* R, int64_t k, int64_t n) {
+__global__ void extract_r_kernel(const T* W, int64_t ldw, T* R, int64_t k, int64_t n, const double* unscale) {
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const double s = unscale ? unscale[1] : 1.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k * n; i += step) {
     const int64_t r = i / n, c = i - r * n;
-    R[i] = (c >= r) ? W[r * ldw + c] : Num<T>::zero();
+    R[i] = (c >= r) ? Num<T>::scale(W[r * ldw + c], s) : Num<T>::zero();
   }
 }
 // Q := [I_k; 0] (m x k, ld)
@@ -269,7 +299,7 @@ static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct QrLayout {
   int64_t k, ldw, ldv, npanels;
-  size_t off_w, off_v, off_t, off_w1, off_w2, total;
+  size_t off_w, off_v, off_t, off_w1, off_w2, off_sc, total;
 };
 
 static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
@@ -286,6 +316,7 @@ static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
   L.off_t = o;  o += align_up((size_t)L.npanels * QR_NB * QR_NB * es);
   L.off_w1 = o; o += align_up((size_t)QR_NB * (wide + 2) * es);
   L.off_w2 = o; o += align_up((size_t)QR_NB * (wide + 2) * es);
+  L.off_sc = o; o += 256;  // [0] amax bits, [1] scale, [2] 1/scale
   L.total = o;
   return L;
 }
@@ -330,14 +361,19 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // panel factorisation + T factor: ~ (2 jb^2 + jb^2) mr real flops, x4 complex
+  ProfScope prof(KC_QR_PANEL, st, (sizeof(T) == 16 ? 4.0 : 1.0) * 3.0 * (double)mr * a.jb * a.jb);
   TNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
   ++g_launches;
   return 0;
 }
 
+// scale_mode 0: factor A as it is; 1: factor 2^e A (e from max|A|, so no dot product can overflow) and
+// return R of A itself; 2: as 1 but return R of the SCALED matrix and the factors in scale_out[0..1]
+// (scale, 1/scale) -- used by svd.cu, which folds 1/scale into the singular values.
 template <typename T>
 static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws,
-                   cudaStream_t st) {
+                   int scale_mode, double** scale_out, cudaStream_t st) {
   const QrLayout L = qr_layout(dtype, m, n);
   char* base = (char*)ws;
   T* W = (T*)(base + L.off_w);
@@ -346,7 +382,18 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
   T* W1 = (T*)(base + L.off_w1);
   T* W2 = (T*)(base + L.off_w2);
   const int64_t k = L.k;
-  copy2d_kernel<T><<<blocks_for(m * n), 256, 0, st>>>((const T*)A, lda, W, L.ldw, m, n);
+  double* sc = nullptr;
+  if (scale_mode != 0) {
+    unsigned long long* bits = (unsigned long long*)(base + L.off_sc);
+    sc = (double*)(base + L.off_sc) + 1;
+    TNB_CUDA_CHECK(cudaMemsetAsync(bits, 0, sizeof(unsigned long long), st));
+    amax_kernel<T><<<blocks_for(m * n), 256, 0, st>>>((const T*)A, lda, m, n, bits);
+    TNB_LAUNCH_CHECK();
+    pow2_scale_kernel<<<1, 1, 0, st>>>(bits, sc);
+    TNB_LAUNCH_CHECK();
+    if (scale_out) *scale_out = sc;
+  }
+  copy2d_kernel<T><<<blocks_for(m * n), 256, 0, st>>>((const T*)A, lda, W, L.ldw, m, n, sc);
   TNB_LAUNCH_CHECK();
   // V must be zero outside the panels' own columns/rows it writes (rows above a panel)
   TNB_CUDA_CHECK(cudaMemsetAsync(V, 0, (size_t)m * L.ldv * sizeof(T), st));
@@ -372,7 +419,7 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
     }
   }
   if (R) {
-    extract_r_kernel<T><<<blocks_for(k * n), 256, 0, st>>>(W, L.ldw, (T*)R, k, n);
+    extract_r_kernel<T><<<blocks_for(k * n), 256, 0, st>>>(W, L.ldw, (T*)R, k, n, scale_mode == 1 ? sc : nullptr);
     TNB_LAUNCH_CHECK();
   }
   if (Q) {
@@ -399,9 +446,10 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
 }
 
 // internal entry used by svd.cu as well
-int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, cudaStream_t st) {
-  if (dtype == TNB_F64) return qr_impl<double>(dtype, m, n, A, lda, Q, R, ws, st);
-  return qr_impl<cplx>(dtype, m, n, A, lda, Q, R, ws, st);
+int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, int scale_mode,
+       double** scale_out, cudaStream_t st) {
+  if (dtype == TNB_F64) return qr_impl<double>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st);
+  return qr_impl<cplx>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st);
 }
 size_t qr_workspace(int dtype, int64_t m, int64_t n) { return qr_layout(dtype, m, n).total; }
 
@@ -419,5 +467,5 @@ extern "C" int tnb_qr(int dtype, int64_t m, int64_t n, const void* A, int64_t ld
   if (m == 0 || n == 0) return 0;
   if (!A || !ws) return TNB_E_ARG;
   if (ws_bytes < tnb::qr_workspace(dtype, m, n)) return TNB_E_WORKSPACE;
-  return tnb::qr(dtype, m, n, A, lda, Q, R, ws, (cudaStream_t)stream);
+  return tnb::qr(dtype, m, n, A, lda, Q, R, ws, 1, nullptr, (cudaStream_t)stream);
 }

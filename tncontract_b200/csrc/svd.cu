@@ -50,7 +50,8 @@ namespace tnb {
 int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
          int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
          int64_t sC, int64_t batch, cudaStream_t st);
-int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, cudaStream_t st);
+int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, int scale_mode,
+       double** scale_out, cudaStream_t st);
 size_t qr_workspace(int dtype, int64_t m, int64_t n);
 int permute_view(int dtype, const void* in, int rank, const int64_t* oshape, const int64_t* istride, void* out,
                  double ar, double ai, int conj, cudaStream_t st);
@@ -65,6 +66,8 @@ struct JacobiFlags {
   unsigned long long maxoff_bits;  // max off-diagonal cosine of the sweep in flight (double bits)
   int converged;
   int sweeps;  // completed sweeps (stops counting once converged)
+  int bad;     // a non-finite singular value was produced (NaN / Inf input)
+  int pad;
 };
 
 struct JacobiArgs {
@@ -313,23 +316,43 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const T* X, int64_t ld, i
   if (lane == 0) sigma[row] = sqrt(acc);
 }
 
-// descending rank by counting (stable): perm[rank] = j, S[rank] = sigma[j]
-__global__ void __launch_bounds__(256) rank_kernel(const double* sigma, int64_t n, int32_t* perm, double* S) {
+// descending rank by counting (stable): perm[rank] = j, S[rank] = sigma[j] * scale[0].
+// Non-finite values rank last (so perm is always a permutation) and raise flags->bad.
+__global__ void __launch_bounds__(256) rank_kernel(const double* sigma, int64_t n, int32_t* perm, double* S,
+                                                   const double* scale, JacobiFlags* flags) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const double sj = sigma[j];
+  const double raw = sigma[j];
+  const bool okj = isfinite(raw);
+  const double sj = okj ? raw : -1.0;
   int64_t r = 0;
   for (int64_t i = 0; i < n; ++i) {
-    const double si = sigma[i];
+    const double ri = sigma[i];
+    const double si = isfinite(ri) ? ri : -1.0;
     r += (si > sj || (si == sj && i < j)) ? 1 : 0;
   }
   perm[r] = (int32_t)j;
-  S[r] = sj;
+  const double sc = scale[0];
+  S[r] = raw * sc;
+  if (!okj || !isfinite(sc)) flags->bad = 1;
+}
+
+// nrm[0] = |R|_F was written by norm2; x *= 1/nrm[0] (x *= 1 for a zero or non-finite norm,
+// nrm[0] is then reset to 1 so that the singular values are scaled back consistently)
+template <typename T>
+__global__ void unit_scale_kernel(T* x, int64_t n, double* nrm, double* scale_out, const double* qscale) {
+  const double v = nrm[0];
+  const bool ok = isfinite(v) && v > 0.0;
+  const double inv = ok ? 1.0 / v : 1.0;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) x[i] = Num<T>::scale(x[i], inv);
+  // singular values of A = (row norms) * |R|_F / 2^e; a non-finite norm propagates and is reported
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[0] = (ok ? v : (v == 0.0 ? 1.0 : v)) * qscale[1];
 }
 
 // out[k, c] = f(in[perm[k], c])            (transpose == 0, out ld = ldo)
 // out[c, k] = f(in[perm[k], c])            (transpose == 1)
-// f: optional conjugation and division by S[k] (zero singular value -> zero vector)
+// f: optional conjugation and division by S[perm[k]] (S = UNSORTED row norms; zero -> zero vector)
 template <typename T>
 __global__ void gather_rows_kernel(const T* in, int64_t ldi, const int32_t* perm, const double* S, T* out, int64_t ldo,
                                    int64_t n, int64_t L, int conj, int scale, int transpose) {
@@ -339,7 +362,7 @@ __global__ void gather_rows_kernel(const T* in, int64_t ldi, const int32_t* perm
     if (transpose) { c = i / n; k = i - c * n; } else { k = i / L; c = i - k * L; }
     T v = in[(int64_t)perm[k] * ldi + c];
     if (conj) v = Num<T>::conj(v);
-    if (scale) { const double s = S[k]; v = Num<T>::scale(v, s > 0.0 ? 1.0 / s : 0.0); }
+    if (scale) { const double s = S[perm[k]]; v = Num<T>::scale(v, s > 0.0 ? 1.0 / s : 0.0); }
     if (transpose) out[c * ldo + k] = v; else out[k * ldo + c] = v;
   }
 }
@@ -364,7 +387,7 @@ static inline unsigned blocks_for(int64_t n) {
 
 struct SvdLayout {
   int64_t k, mq, nq;  // QR problem: mq x nq with nq == k
-  size_t off_ah, off_q, off_r, off_x, off_v, off_vs, off_sig, off_perm, off_flags, off_qr, total;
+  size_t off_ah, off_q, off_r, off_x, off_v, off_vs, off_sig, off_perm, off_flags, off_nrm, off_qr, total;
 };
 
 static SvdLayout svd_layout(int dtype, int64_t m, int64_t n) {
@@ -383,6 +406,7 @@ static SvdLayout svd_layout(int dtype, int64_t m, int64_t n) {
   L.off_sig = o;   o += align_up((size_t)L.k * sizeof(double));
   L.off_perm = o;  o += align_up((size_t)L.k * sizeof(int32_t));
   L.off_flags = o; o += align_up(sizeof(JacobiFlags));
+  L.off_nrm = o;   o += align_up(1024 * sizeof(double));  // [0] |R|_F, [1] scale, [8..] norm2 workspace
   L.off_qr = o;    o += align_up(qr_workspace(dtype, L.mq, L.nq));
   L.total = o;
   return L;
@@ -443,6 +467,9 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
   while (queued < MAX_SWEEPS) {
     const int batch = (queued == 0) ? 5 : 2;
     for (int s = 0; s < batch; ++s) {
+      // executed flops of one sweep: per pair and round, a JP x JP Gram over L and W applied over L + n
+      ProfScope prof(KC_JACOBI, st, (cplx ? 8.0 : 2.0) * (double)JP * JP * (2.0 * (double)L + (double)n) *
+                                        (double)npairs * (double)rounds);
       for (int r = 0; r < rounds; ++r) {
         a.round = r;
         int rc = launch_round<T>(a, npairs, smem, st);
@@ -474,18 +501,20 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   double* sig = (double*)(base + L.off_sig);
   int32_t* perm = (int32_t*)(base + L.off_perm);
   JacobiFlags* flags = (JacobiFlags*)(base + L.off_flags);
+  double* nrm = (double*)(base + L.off_nrm);
   void* qr_ws = base + L.off_qr;
   const bool wide = m < n;
   int rc;
+  double* qscale = nullptr;  // device: [0] power-of-two scale applied before the QR, [1] its inverse
   if (!wide) {
-    rc = qr(dtype, m, n, A, lda, Q, R, qr_ws, st);
+    rc = qr(dtype, m, n, A, lda, Q, R, qr_ws, 2, &qscale, st);
     if (rc) return rc;
   } else {
     T* AH = (T*)(base + L.off_ah);  // A^H, n x m contiguous
     const int64_t sh[2] = {n, m}, is[2] = {1, lda};
     rc = permute_view(dtype, A, 2, sh, is, AH, 1.0, 0.0, 1, st);
     if (rc) return rc;
-    rc = qr(dtype, n, m, AH, m, Q, R, qr_ws, st);
+    rc = qr(dtype, n, m, AH, m, Q, R, qr_ws, 2, &qscale, st);
     if (rc) return rc;
   }
   {  // Xt = conj(R): row j of Xt is column j of X = R^H
@@ -493,13 +522,21 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     rc = permute_view(dtype, R, 2, sh, is, Xt, 1.0, 0.0, 1, st);
     if (rc) return rc;
   }
+  {  // Jacobi works on Gram matrices (squared magnitudes): bring X to unit Frobenius norm first
+    tnb_tensor_t xd;
+    xd.ptr = Xt; xd.dtype = dtype; xd.rank = 1; xd.shape[0] = k * k; xd.stride[0] = 1;
+    rc = tnb_norm2(&xd, nrm, nrm + 8, 1016 * sizeof(double), st);
+    if (rc) return rc;
+    unit_scale_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k * k, nrm, nrm + 1, qscale);
+    TNB_LAUNCH_CHECK();
+  }
   eye_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Vt, k);
   TNB_LAUNCH_CHECK();
   rc = jacobi<T>(Xt, k, k, Vt, k, flags, sweeps_out, st);
   if (rc) return rc;
   row_norm_kernel<T><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(Xt, k, k, k, sig);
   TNB_LAUNCH_CHECK();
-  rank_kernel<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(sig, k, perm, S);
+  rank_kernel<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(sig, k, perm, S, nrm + 1, flags);
   TNB_LAUNCH_CHECK();
   // Vs[j, :] = Vt[perm[j], :]  (column j of the sorted V, as a row)
   gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Vt, k, perm, S, Vs, k, k, k, 0, 0, 0);
@@ -507,7 +544,7 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   if (!wide) {
     // A = Q R, R = V Sigma Ux^H:  U = Q V,  Vh = Ux^H = conj(Y^T) / sigma
     if (Vh) {
-      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, S, (T*)Vh, n, k, k, 1, 1, 0);
+      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, (T*)Vh, n, k, k, 1, 1, 0);
       TNB_LAUNCH_CHECK();
     }
     if (U) {
@@ -517,7 +554,7 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   } else {
     // A = R^H Q^H = Ux Sigma (Q V)^H:  U = Y / sigma,  Vh = conj(Vs) Q^H
     if (U) {
-      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, S, (T*)U, k, k, k, 0, 1, 1);
+      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, (T*)U, k, k, k, 0, 1, 1);
       TNB_LAUNCH_CHECK();
     }
     if (Vh) {
@@ -525,7 +562,10 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       if (rc) return rc;
     }
   }
-  return 0;
+  JacobiFlags h;
+  TNB_CUDA_CHECK(cudaMemcpyAsync(&h, flags, sizeof(JacobiFlags), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return h.bad ? TNB_E_NOCONV : 0;  // NaN / Inf in the input: numpy.linalg.svd raises LinAlgError too
 }
 
 }  // namespace tnb
