@@ -100,6 +100,11 @@ int tnb_trace(const tnb_tensor_t* x, int axis1, int axis2, void* out, void* stre
 /* widen a real vector/tensor to complex128 (dtype promotion inside np.tensordot) */
 int tnb_real_to_complex(const double* x, int64_t n, void* out, void* stream);
 
+/* out[i] = U[0,1) from a counter-based generator (splitmix64 of key + (offset+i)*golden):
+ * stands in for np.random.rand (onedim_utils.py:47) when the batched path creates its
+ * synthetic networks on the owning GPU; reproducible element-wise on the host. */
+int tnb_fill_uniform(double* out, int64_t n, unsigned long long key, unsigned long long offset, void* stream);
+
 /* ---- GEMM: the BLAS call under np.tensordot (tensor.py:735) ---------------
  * C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b], row-major, b < batch,
  * X[b] = X + b*strideX (elements).  FP64 / complex128 on DMMA tensor cores. */

@@ -1,0 +1,166 @@
+"""GPU: the BASELINE.json configurations at (or near) full size, checked through
+size-independent properties (the oracle would take minutes to hours here):
+factor products and isometry, norm preservation, canonical-form identities,
+kept bond dimensions, idempotence of compression, linearity of contraction."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tn():
+    import tncontract_b200 as tn
+    return tn
+
+
+def _rel(a, b):
+    return np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / np.linalg.norm(np.asarray(b).ravel())
+
+
+def test_cfg2_random_mps_canonise_compress():
+    """cfg 2: random MPS N=50, d=2, chi=64 float64 (init_mps_random, seed 1):
+    left/right canonisation, svd_compress to chi=32."""
+    tn = _tn()
+    od = tn.onedim
+    np.random.seed(1)
+    psi = od.init_mps_random(50, 2, 64)
+    assert psi.bonddims() == [1] + [64] * 49 + [1]
+    n0 = psi.norm()
+    ip0 = od.inner_product_mps(psi, psi)
+    a = psi.copy(); a.left_canonise(qr_decomposition=True)
+    assert a.check_canonical_form(threshold=1e-9, print_output=False) == (49, 49)
+    assert abs(a.norm(canonical_form="left") - n0) < 1e-10 * n0
+    assert abs(od.inner_product_mps(psi, a) - ip0) < 1e-10 * abs(ip0)
+    b = psi.copy(); b.right_canonise()
+    assert b.check_canonical_form(threshold=1e-9, print_output=False) == (0, 0)
+    assert abs(b.norm(canonical_form="right") - n0) < 1e-10 * n0
+    expect = [min(64, 2 ** i, 2 ** (50 - i)) for i in range(51)]
+    assert b.bonddims() == expect
+    c = psi.copy(); c.svd_compress(chi=32)
+    assert c.bonddims() == [min(32, 2 ** i, 2 ** (50 - i)) for i in range(51)]   # SURVEY 8d cfg 2
+    assert [t.labels for t in c][0] == ["right", "phys", "left"] and c[7].labels == ["phys", "right", "left"]
+    assert c.check_canonical_form(threshold=1e-9, print_output=False) == (0, 0)
+    # compression is a projection: compressing again changes nothing (idempotence)
+    d = c.copy(); d.svd_compress(chi=32)
+    assert abs(od.inner_product_mps(c, d) - od.inner_product_mps(c, c)) < 1e-10 * abs(od.inner_product_mps(c, c))
+    # and it never increases the norm; overlap with the original is real positive
+    assert c.norm() <= n0 * (1 + 1e-12)
+    ov = od.inner_product_mps(psi, c)
+    assert abs(ov - c.norm() ** 2) < 1e-9 * abs(ov)   # <psi|P psi> = |P psi|^2 for the (quasi-optimal) projector
+
+
+@pytest.mark.parametrize("shape", [(3072, 1536), (1024, 1536)])
+def test_cfg3_bulk_site_factorisations(shape):
+    """cfg 3 bulk site: QR of the 3072x1536 and SVD of the 1024x1536 complex128 matricisations."""
+    from tncontract_b200 import devarray as dv
+    rng = np.random.default_rng(3)
+    m, n = shape
+    a = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    A = dv.DevArray.from_host(a)
+    k = min(m, n)
+    eye = dv.DevArray.from_host(np.eye(k, dtype=complex))
+    if m >= n:
+        q, r = dv.qr(A)
+        assert _rel(dv.tensordot(q, r, [1], [0]), a) < 1e-12
+        qhq = dv.tensordot(q, q, [0], [0], conj_a=True)
+        assert (qhq - eye).norm() < 1e-11
+        assert np.array_equal(np.tril(np.asarray(r), -1), np.zeros((k, n)))
+    else:
+        u, s, vh = dv.svd(A)
+        s_h = np.asarray(s)
+        assert np.all(np.diff(s_h) <= 0) and s_h[-1] > 0
+        us = dv.diag_scale_cols(u.copy(), s)
+        assert _rel(dv.tensordot(us, vh, [1], [0]), a) < 1e-11
+        assert (dv.tensordot(u, u, [0], [0], conj_a=True) - eye).norm() < 1e-10
+        assert (dv.tensordot(vh, vh, [1], [1], conj_b=True) - eye).norm() < 1e-10
+        # Frobenius identity: sum s^2 = |A|_F^2; largest singular value against a power iteration bound
+        assert abs(np.sum(s_h ** 2) - np.linalg.norm(a) ** 2) < 1e-11 * np.linalg.norm(a) ** 2
+        sref = np.linalg.svd(a, compute_uv=False)
+        assert np.max(np.abs(s_h - sref)) < 1e-10 * sref[0]
+
+
+def test_cfg3_apply_compress_energy_reduced_chain():
+    """cfg 3 with the full bond dimension (chi=512, D=3, complex128) on a shorter
+    chain (N=22 reaches the chi-capped bulk): energy through the MPO, apply +
+    svd_compress, linearity of the apply, and the variational bound."""
+    import bench
+    tn = _tn()
+    od = tn.onedim
+    n, d, chi = 22, 2, 512
+    sites = bench.make_host_sites(n, d, chi, seed=2)
+    W = bench.tfi_w()
+    ws = [W[2] if i == 0 else (W[:, 0] if i == n - 1 else W) for i in range(n)]
+    wl = [["right", "physout", "physin"] if i == 0 else (["left", "physout", "physin"] if i == n - 1 else
+                                                         ["left", "right", "physout", "physin"]) for i in range(n)]
+    psi = od.MatrixProductState([tn.Tensor(a, ["phys", "left", "right"]) for a in sites])
+    psi.left_canonise(qr_decomposition=True, normalise=True)
+    assert abs(psi.norm() - 1.0) < 1e-10
+    H = od.MatrixProductOperator([tn.Tensor(w, l) for w, l in zip(ws, wl)], "left", "right", "physout", "physin")
+    phi = od.contract_mps_mpo(psi, H)
+    assert max(phi.bonddims()) == 3 * chi and all(t.labels == ["left", "physout", "right"] for t in phi)
+    e = od.inner_product_mps(psi, phi)
+    assert abs(e.imag) < 1e-10 * abs(e)                     # H is Hermitian
+    h2 = od.inner_product_mps(phi, phi)                     # <H^2> >= <H>^2
+    assert h2.real >= e.real ** 2 - 1e-9 and abs(h2.imag) < 1e-9 * abs(h2)
+    # linearity: H(2 psi) = 2 H psi
+    psi2 = psi.copy(); psi2[5].data *= 2.0
+    assert abs(od.inner_product_mps(phi, od.contract_mps_mpo(psi2, H)) - 2 * h2) < 1e-10 * abs(h2)
+    c = phi.copy(); c.svd_compress(chi=chi)
+    assert max(c.bonddims()) == chi
+    assert c.bonddims() == [min(chi, 2 ** i, 2 ** (n - i)) for i in range(n + 1)]
+    assert c.check_canonical_form(threshold=1e-8, print_output=False) == (0, 0)
+    # H psi has Schmidt rank <= 2^min(i, n-i) <= chi on every bond here, so compression is lossless
+    assert abs(od.inner_product_mps(phi, c) - h2) < 1e-10 * abs(h2)
+    assert abs(c.norm() ** 2 - h2.real) < 1e-10 * abs(h2)
+    assert abs(od.inner_product_mps(psi, c) - e) < 1e-10 * max(abs(e), 1.0)
+
+
+def test_cfg4_one_network():
+    """cfg 4 unit of work: one pair of random float64 MPS (N=64, d=4, chi=128):
+    overlap, norm, svd_compress(chi=64)."""
+    tn = _tn()
+    od = tn.onedim
+    rng = np.random.default_rng(3)
+    bonds = [1] + [128] * 63 + [1]
+    mk = lambda: od.MatrixProductState([tn.Tensor(rng.random((4, bonds[i], bonds[i + 1])) / 16.0,
+                                                   ["phys", "left", "right"]) for i in range(64)])
+    a, b = mk(), mk()
+    ab = od.inner_product_mps(a, b)
+    ba = od.inner_product_mps(b, a)
+    assert abs(ab - ba) < 1e-10 * abs(ab)                   # real symmetric
+    na = a.norm()
+    assert abs(na ** 2 - od.inner_product_mps(a, a)) < 1e-10 * na ** 2
+    assert abs(ab) <= na * b.norm() * (1 + 1e-12)           # Cauchy-Schwarz
+    c = a.copy(); c.svd_compress(chi=64)
+    assert max(c.bonddims()) == 64
+    assert c.check_canonical_form(threshold=1e-8, print_output=False) == (0, 0)
+    assert c.norm() <= na * (1 + 1e-12)
+    ov = od.inner_product_mps(a, c) / (na * c.norm())
+    assert 0.5 < ov <= 1 + 1e-12                            # U[0,1) states are close to rank one
+
+
+def test_cfg5_peps_boundary_reduced():
+    """cfg 5 at reduced size (6x6, D=3 -> double-layer bond 9, chi=32; the 8x8,
+    D=4, chi=256 case needs a 65536x4096 SVD per site): boundary-MPS value against the
+    chi = full contraction, bond profile, and symmetry under lattice reflection."""
+    tn = _tn()
+    td = tn.twodim
+    rng = np.random.default_rng(4)
+    L, D = 6, 3
+    grid = []
+    for r in range(L):
+        row = []
+        for c in range(L):
+            shape = (2, 1 if r == 0 else D, 1 if r == L - 1 else D, 1 if c == 0 else D, 1 if c == L - 1 else D)
+            row.append(tn.Tensor(rng.standard_normal(shape) / D, ["phys", "up", "down", "left", "right"]))
+        grid.append(row)
+    peps = td.SquareLatticePEPS(grid)
+    net = td.inner_product_peps(peps, peps, contract_virtual=False)
+    cols = net.mps_contract(32, return_all_columns=True)
+    assert [max(c.bonddims()) for c in cols[:-1]] == [9, 32, 32, 32, 32]
+    v32 = np.float64(cols[-1].data)
+    v81 = np.float64(net.mps_contract(81).data)
+    assert v32 > 0 and v81 > 0                              # <psi|psi>
+    assert abs(v32 - v81) < 2e-2 * v81
+    mirrored = net.fliplr().mps_contract(81)
+    assert abs(np.float64(mirrored.data) - v81) < 1e-9 * v81

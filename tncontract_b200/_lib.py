@@ -51,6 +51,7 @@ SIGNATURES = {
     "tnb_diag_scale": (_c.c_int, [_c.c_int, _vp, _i64, _i64, _i64, _vp, _c.c_int, _c.c_int, _vp]),
     "tnb_trace": (_c.c_int, [_pd, _c.c_int, _c.c_int, _vp, _vp]),
     "tnb_real_to_complex": (_c.c_int, [_vp, _i64, _vp, _vp]),
+    "tnb_fill_uniform": (_c.c_int, [_vp, _i64, _c.c_ulonglong, _c.c_ulonglong, _vp]),
     "tnb_gemm": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _i64, _i64, _i64, _pdbl, _vp, _i64, _i64, _vp, _i64, _i64,
                             _pdbl, _vp, _i64, _i64, _i64, _vp]),
     "tnb_tensordot_workspace": (_sz, [_pd, _pd, _c.c_int, _pi32, _pi32]),

@@ -349,3 +349,28 @@ extern "C" int tnb_device_info(int* sms, int* major, int* minor) {
   if (minor) TNB_CUDA_CHECK(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
   return 0;
 }
+
+// ---- counter-based uniform fill (batched-path input generation on the owning GPU) ------------
+// out[i] = U[0,1) from splitmix64(key + (offset + i) * golden): any element can be regenerated on the
+// host (tests/, batch.py:host_uniform) without replaying a stream.
+namespace tnb {
+__global__ void fill_uniform_kernel(double* out, int64_t n, unsigned long long key, unsigned long long offset) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    unsigned long long z = key + (offset + (unsigned long long)i) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    out[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  }
+}
+}  // namespace tnb
+
+extern "C" int tnb_fill_uniform(double* out, int64_t n, unsigned long long key, unsigned long long offset,
+                                void* stream) {
+  if (!out || n < 0) return TNB_E_ARG;
+  if (n == 0) return 0;
+  tnb::fill_uniform_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(out, n, key, offset);
+  TNB_LAUNCH_CHECK();
+  return 0;
+}

@@ -34,6 +34,11 @@ struct GemmArgs {
   double alpha_r, alpha_i, beta_r, beta_i;
   int conjA, conjB;
   int tiles_m, tiles_n;
+  // split-K: blockIdx.z owns K range [z*k_per_split, ...) and writes its raw partial product
+  // (alpha = 1, beta = 0) to part + z*M*N (row-major, ld = N); splitk_reduce_kernel finishes.
+  int splits;
+  int64_t k_per_split;
+  void* part;
 };
 
 template <bool CPLX, bool SMALL> struct Cfg;
@@ -112,6 +117,13 @@ gemm_kernel(GemmArgs g) {
   const T* A = reinterpret_cast<const T*>(g.A) + bz * g.sA;
   const T* B = reinterpret_cast<const T*>(g.B) + bz * g.sB;
   T* Cg = reinterpret_cast<T*>(g.C) + bz * g.sC;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_per_split;
+  const int64_t kend = (g.splits > 1 && kbeg + g.k_per_split < g.K) ? kbeg + g.k_per_split : g.K;
+  int64_t ldc = g.ldc;
+  if (g.splits > 1) {
+    Cg = reinterpret_cast<T*>(g.part) + (int64_t)blockIdx.z * g.M * g.N;
+    ldc = g.N;
+  }
 
   double acc[MT][NT][CPLX ? 4 : 2];
 #pragma unroll
@@ -121,13 +133,13 @@ gemm_kernel(GemmArgs g) {
 #pragma unroll
       for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[i][j][r] = 0.0;
 
-  const int KT = (int)((g.K + BK - 1) / BK);
+  const int KT = (int)((kend - kbeg + BK - 1) / BK);
 
   auto issue = [&](int kt) {
     if (kt < KT) {
       const int s = kt % STAGES;
-      load_tile<T, CPLX, A_KC, VEC, BM, BK, THREADS>(sA + s * LA::ELEMS, A, g.lda, m0, (int64_t)kt * BK, g.M, g.K, tid);
-      load_tile<T, CPLX, B_KC, VEC, BN, BK, THREADS>(sB + s * LB::ELEMS, B, g.ldb, n0, (int64_t)kt * BK, g.N, g.K, tid);
+      load_tile<T, CPLX, A_KC, VEC, BM, BK, THREADS>(sA + s * LA::ELEMS, A, g.lda, m0, kbeg + (int64_t)kt * BK, g.M, kend, tid);
+      load_tile<T, CPLX, B_KC, VEC, BN, BK, THREADS>(sB + s * LB::ELEMS, B, g.ldb, n0, kbeg + (int64_t)kt * BK, g.N, kend, tid);
     }
     cp_async_commit();
   };
@@ -182,7 +194,8 @@ gemm_kernel(GemmArgs g) {
   cp_async_wait<0>();
 
   // epilogue: thread owns C[row = gq][cols 2*tq, 2*tq+1] of every 8x8 tile
-  const bool has_beta = (g.beta_r != 0.0 || g.beta_i != 0.0);
+  const bool has_beta = (g.beta_r != 0.0 || g.beta_i != 0.0) && g.splits <= 1;
+  const double alpha_r = g.splits > 1 ? 1.0 : g.alpha_r, alpha_i = g.splits > 1 ? 0.0 : g.alpha_i;
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
     const int64_t row = m0 + wm * WM + i * 8 + gq;
@@ -191,9 +204,9 @@ gemm_kernel(GemmArgs g) {
     for (int j = 0; j < NT; ++j) {
       const int64_t col = n0 + wn * WN + j * 8 + 2 * tq;
       if (col >= g.N) continue;
-      T* dst = Cg + row * g.ldc + col;
+      T* dst = Cg + row * ldc + col;
       if constexpr (!CPLX) {
-        double v0 = g.alpha_r * acc[i][j][0], v1 = g.alpha_r * acc[i][j][1];
+        double v0 = alpha_r * acc[i][j][0], v1 = alpha_r * acc[i][j][1];
         if (has_beta) {
           v0 += g.beta_r * dst[0];
           if (col + 1 < g.N) v1 += g.beta_r * dst[1];
@@ -205,7 +218,7 @@ gemm_kernel(GemmArgs g) {
           if (col + 1 < g.N) dst[1] = v1;
         }
       } else {
-        const double2 al = make_double2(g.alpha_r, g.alpha_i), be = make_double2(g.beta_r, g.beta_i);
+        const double2 al = make_double2(alpha_r, alpha_i), be = make_double2(g.beta_r, g.beta_i);
         double2 v0 = cmul(al, make_double2(acc[i][j][0], acc[i][j][2]));
         double2 v1 = cmul(al, make_double2(acc[i][j][1], acc[i][j][3]));
         if (has_beta) {
@@ -242,11 +255,32 @@ static int launch_gemm(GemmArgs& g, int64_t batch, cudaStream_t st) {
     h.A = (const char*)g.A + b0 * g.sA * ES;
     h.B = (const char*)g.B + b0 * g.sB * ES;
     h.C = (char*)g.C + b0 * g.sC * ES;
-    dim3 grid((unsigned)(g.tiles_m * g.tiles_n), (unsigned)nb);
+    dim3 grid((unsigned)(g.tiles_m * g.tiles_n), (unsigned)nb, (unsigned)(g.splits > 1 ? g.splits : 1));
     kern<<<grid, threads, smem, st>>>(h);
     TNB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+// C = alpha * sum_z part[z] + beta * C  (deterministic: fixed summation order)
+template <typename T>
+__global__ void splitk_reduce_kernel(const T* part, int splits, int64_t M, int64_t N, T* C, int64_t ldc, double ar,
+                                     double ai, double br, double bi) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const bool has_beta = (br != 0.0 || bi != 0.0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += step) {
+    T s = part[i];
+    for (int z = 1; z < splits; ++z) s = Num<T>::add(s, part[(int64_t)z * M * N + i]);
+    const int64_t r = i / N, c = i - r * N;
+    T& dst = C[r * ldc + c];
+    if constexpr (sizeof(T) == 8) {
+      dst = has_beta ? ar * s + br * dst : ar * s;
+    } else {
+      T v = cmul(make_double2(ar, ai), s);
+      if (has_beta) v = cadd(v, cmul(make_double2(br, bi), dst));
+      dst = v;
+    }
+  }
 }
 
 template <bool CPLX, bool SMALL, bool VEC>
@@ -271,9 +305,21 @@ __global__ void scale_c_kernel(T* C, int64_t M, int64_t N, int64_t ldc, int64_t 
   }
 }
 
+int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
+            int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
+            int64_t sC, int64_t batch, void* splitk_ws, size_t splitk_bytes, cudaStream_t st);
+
 int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
          int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
          int64_t sC, int64_t batch, cudaStream_t st) {
+  return gemm_ws(dtype, opA, opB, M, N, K, ar, ai, A, lda, sA, B, ldb, sB, br, bi, C, ldc, sC, batch, nullptr, 0, st);
+}
+
+// As gemm(); with a scratch buffer, problems that have few C tiles but a long K (the V^H A products of
+// the blocked QR, Gram-like shapes) are split along K over grid.z and reduced in a second kernel.
+int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
+            int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
+            int64_t sC, int64_t batch, void* splitk_ws, size_t splitk_bytes, cudaStream_t st) {
   if (M < 0 || N < 0 || K < 0 || batch < 0) return TNB_E_ARG;
   if (M == 0 || N == 0 || batch == 0) return 0;
   if (!C) return TNB_E_ARG;
@@ -301,6 +347,7 @@ int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar
   g.lda = lda; g.ldb = ldb; g.ldc = ldc;
   g.sA = sA; g.sB = sB; g.sC = sC;
   g.alpha_r = ar; g.alpha_i = ai; g.beta_r = br; g.beta_i = bi;
+  g.splits = 1; g.k_per_split = K; g.part = nullptr;
   g.conjA = cplx && (opA == TNB_OP_C || opA == TNB_OP_J);
   g.conjB = cplx && (opB == TNB_OP_C || opB == TNB_OP_J);
   // op N on A: stored M x K (k contiguous). op T/C: stored K x M (m contiguous).
@@ -310,17 +357,43 @@ int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar
   // skinny problems: smaller tiles waste fewer DMMAs and fill more SMs
   const int64_t big_tiles = cplx ? ((M + 127) / 128) * ((N + 63) / 64) : ((M + 127) / 128) * ((N + 127) / 128);
   const bool small = (M <= 64) || (N <= (cplx ? 32 : 64)) || (big_tiles * batch < (int64_t)sm_count());
+  if (splitk_ws && batch == 1) {
+    const int64_t bm = small ? 64 : 128, bn = cplx ? (small ? 32 : 64) : (small ? 64 : 128), bk = cplx ? 8 : 16;
+    const int64_t tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
+    int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;  // aim at ~2 CTAs per SM
+    const int64_t max_by_k = K / (bk * 16);                       // keep >= 16 k-steps per split
+    const int64_t max_by_ws = (int64_t)(splitk_bytes / ((size_t)M * N * (cplx ? 16 : 8)));
+    if (want > max_by_k) want = max_by_k;
+    if (want > max_by_ws) want = max_by_ws;
+    if (want > 64) want = 64;
+    if (want >= 2) {
+      int64_t kps = (K + want - 1) / want;
+      kps = ((kps + bk - 1) / bk) * bk;
+      g.splits = (int)((K + kps - 1) / kps);
+      g.k_per_split = kps;
+      g.part = splitk_ws;
+    }
+  }
+  auto finish = [&](int rc) -> int {
+    if (rc != 0 || g.splits <= 1) return rc;
+    int64_t blocks = (M * N + 255) / 256;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    if (cplx) splitk_reduce_kernel<double2><<<(unsigned)blocks, 256, 0, st>>>((const double2*)g.part, g.splits, M, N, (double2*)C, ldc, ar, ai, br, bi);
+    else splitk_reduce_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)g.part, g.splits, M, N, (double*)C, ldc, ar, ai, br, bi);
+    TNB_LAUNCH_CHECK();
+    return 0;
+  };
   if (cplx) {
-    return small ? dispatch_layout<true, true, true>(g, a_kc, b_kc, batch, st)
-                 : dispatch_layout<true, false, true>(g, a_kc, b_kc, batch, st);
+    return finish(small ? dispatch_layout<true, true, true>(g, a_kc, b_kc, batch, st)
+                        : dispatch_layout<true, false, true>(g, a_kc, b_kc, batch, st));
   }
   const bool vec = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                    (sA % 2 == 0 || batch == 1) && (sB % 2 == 0 || batch == 1);
   if (vec)
-    return small ? dispatch_layout<false, true, true>(g, a_kc, b_kc, batch, st)
-                 : dispatch_layout<false, false, true>(g, a_kc, b_kc, batch, st);
-  return small ? dispatch_layout<false, true, false>(g, a_kc, b_kc, batch, st)
-               : dispatch_layout<false, false, false>(g, a_kc, b_kc, batch, st);
+    return finish(small ? dispatch_layout<false, true, true>(g, a_kc, b_kc, batch, st)
+                        : dispatch_layout<false, false, true>(g, a_kc, b_kc, batch, st));
+  return finish(small ? dispatch_layout<false, true, false>(g, a_kc, b_kc, batch, st)
+                      : dispatch_layout<false, false, false>(g, a_kc, b_kc, batch, st));
 }
 
 }  // namespace tnb

@@ -25,6 +25,9 @@ namespace tnb {
 int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
          int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
          int64_t sC, int64_t batch, cudaStream_t st);
+int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
+            int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
+            int64_t sC, int64_t batch, void* splitk_ws, size_t splitk_bytes, cudaStream_t st);
 
 constexpr int QR_NB = 32;
 constexpr int QR_THREADS = 256;
@@ -33,8 +36,8 @@ constexpr int QR_WARPS = QR_THREADS / 32;
 struct QrPanelArgs {
   void* W;        // working copy of A, m x n, ld = ldw
   void* V;        // explicit Householder vectors, m x k, ld = ldv
-  void* T;        // this panel's jb x jb triangular factor (row-major, ld = QR_NB)
-  int64_t m, ldw, ldv;
+  void* T;        // this panel's jb x jb triangular factor (row-major, ld = ldt)
+  int64_t m, ldw, ldv, ldt;
   int64_t j0;     // first column / diagonal row of the panel
   int jb;         // panel width (<= QR_NB)
   int rows_per;   // panel rows owned by each CTA of the cluster
@@ -82,6 +85,9 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
   }
   __syncthreads();
 
+  // stage[r][c]: all CTAs' partial dots of the current column step, copied from DSMEM in ONE round trip
+  T* stage = Z;  // QR_NB x QR_NB scratch: Z is only needed after the column loop (C <= 16 ranks <= QR_NB rows)
+  __shared__ T rowv_l[QR_NB];
   for (int j = 0; j < jb; ++j) {
     const int buf = j & 1;
     // local index of the first row at or below the diagonal
@@ -89,27 +95,62 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
     if (lo < 0) lo = 0;
     const bool own_diag = (j >= r_lo && j < r_lo + nrows);
     const int jl = (int)(j - r_lo);  // local row of the diagonal (valid if own_diag)
-    // ---- partial dots d_c = sum_{r >= j} conj(x_r) A[r, c], c = j..jb-1 ---------------
-    for (int c = j + warp; c < jb; c += QR_WARPS) {
-      T acc = N_::zero();
+    // ---- partial dots d_c = sum_{r >= j} conj(x_r) A[r, c], c = j..jb-1: each warp takes columns
+    //      c = j + warp + 8 i (up to 4) and reduces them together ------------------------------------
+    {
       const T* xj = P + j * a.pitch;
-      const T* xc = P + c * a.pitch;
-      for (int r = lo + lane; r < nrows; r += 32) acc = N_::fma_conj(xj[r], xc[r], acc);
-      acc = warp_sum_t<T>(acc);
+      T acc[4];
+      const T* xc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i] = N_::zero();
+        const int c = j + warp + QR_WARPS * i;
+        xc[i] = P + (c < jb ? c : j) * a.pitch;
+      }
+      for (int r = lo + lane; r < nrows; r += 32) {
+        const T x = xj[r];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = N_::fma_conj(x, xc[i][r], acc[i]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if constexpr (sizeof(T) == 16) {
+            acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o);
+            acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
+          } else {
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+          }
+        }
+      }
       if (lane == 0) {
-        part[buf * QR_NB + c] = acc;
-        if (own_diag) rowv[buf * QR_NB + c] = xc[jl];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = j + warp + QR_WARPS * i;
+          if (c < jb) {
+            part[buf * QR_NB + c] = acc[i];
+            if (own_diag) rowv[buf * QR_NB + c] = xc[i][jl];
+          }
+        }
       }
     }
     cluster.sync();
-    // ---- every CTA forms the same reflector parameters -------------------------------------
+    // ---- one DSMEM round trip: every CTA copies all partials (and the diagonal row) locally ------
     const int owner = (int)(j / a.rows_per);
-    const T* rowv_owner = cluster.map_shared_rank(rowv, owner);
-    // column j's total first (all warps need it)
+    for (int t = tid; t < C * QR_NB; t += QR_THREADS) {
+      const int rk = t / QR_NB, c = t - rk * QR_NB;
+      if (c >= j && c < jb) stage[rk * QR_NB + c] = cluster.map_shared_rank(part, rk)[buf * QR_NB + c];
+    }
+    if (tid >= QR_THREADS - QR_NB) {
+      const int c = tid - (QR_THREADS - QR_NB);
+      if (c >= j && c < jb) rowv_l[c] = cluster.map_shared_rank(rowv, owner)[buf * QR_NB + c];
+    }
+    __syncthreads();
+    // ---- every thread forms the same reflector parameters ---------------------------------------
     T dj = N_::zero();
-    if (lane < C) dj = cluster.map_shared_rank(part, lane)[buf * QR_NB + j];
-    dj = warp_sum_t<T>(dj);
-    const T alpha = rowv_owner[buf * QR_NB + j];
+    for (int rk = 0; rk < C; ++rk) dj = N_::add(dj, stage[rk * QR_NB + j]);
+    const T alpha = rowv_l[j];
     const double normx2 = N_::real(dj);
     const bool no_tail = (a.j0 + j == a.m - 1);
     double beta;
@@ -131,34 +172,33 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
     }
     if (tid == 0) tau[j] = tau_j;
     const bool active = !(N_::real(tau_j) == 0.0 && N_::abs2(tau_j) == 0.0);
-    // ---- C1: x -> v on column j (all threads over rows), diagonal := beta ------------------
-    {
-      T* xj = P + j * a.pitch;
-      const int lo1 = own_diag ? jl + 1 : lo;
-      for (int r = lo1 + tid; r < nrows; r += QR_THREADS) xj[r] = N_::mul(xj[r], scale);
-      if (own_diag && tid == 0) xj[jl] = N_::from(beta, 0.0);
-    }
-    __syncthreads();
-    // ---- C2: A[:, c] -= conj(tau) * (v^H A[:, c]) * v, c > j ---------------------------------
+    const int lo1 = own_diag ? jl + 1 : lo;
+    // ---- C2: A[:, c] -= conj(tau) * (v^H A[:, c]) * v, c > j, with v = x_j * scale read on the fly ----
     if (active) {
+      const T* xj = P + j * a.pitch;
       for (int c = j + 1 + warp; c < jb; c += QR_WARPS) {
         T dc = N_::zero();
-        if (lane < C) dc = cluster.map_shared_rank(part, lane)[buf * QR_NB + c];
-        dc = warp_sum_t<T>(dc);
-        const T ajc = rowv_owner[buf * QR_NB + c];
+        for (int rk = 0; rk < C; ++rk) dc = N_::add(dc, stage[rk * QR_NB + c]);
+        const T ajc = rowv_l[c];
         // w = v^H A_c = A[j,c] + conj(scale) * (d_c - conj(alpha) * A[j,c])
         const T t1 = N_::sub(dc, N_::mul(N_::conj(alpha), ajc));
         const T w = N_::add(ajc, N_::mul(N_::conj(scale), t1));
         const T f = N_::mul(N_::conj(tau_j), w);
-        const T* vj = P + j * a.pitch;
-        T* xc = P + c * a.pitch;
-        const int lo1 = own_diag ? jl + 1 : lo;
-        for (int r = lo1 + lane; r < nrows; r += 32) xc[r] = N_::sub(xc[r], N_::mul(f, vj[r]));
-        if (own_diag && lane == 0) xc[jl] = N_::sub(xc[jl], f);  // v_j = 1 on the diagonal
+        const T fs = N_::mul(f, scale);
+        T* xcc = P + c * a.pitch;
+        for (int r = lo1 + lane; r < nrows; r += 32) xcc[r] = N_::sub(xcc[r], N_::mul(fs, xj[r]));
+        if (own_diag && lane == 0) xcc[jl] = N_::sub(xcc[jl], f);  // v_j = 1 on the diagonal
       }
     }
     __syncthreads();
+    // ---- C1: x -> v on column j, diagonal := beta (column j is not read again by later columns) ------
+    {
+      T* xj = P + j * a.pitch;
+      for (int r = lo1 + tid; r < nrows; r += QR_THREADS) xj[r] = N_::mul(xj[r], scale);
+      if (own_diag && tid == 0) xj[jl] = N_::from(beta, 0.0);
+    }
   }
+  __syncthreads();
 
   // ---- T factor: Z = strictly-upper part of V^H V, reduced over the cluster --------------------
   for (int idx = warp; idx < jb * jb; idx += QR_WARPS) {
@@ -208,11 +248,11 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
       __syncwarp();
     }
     T* Tg = reinterpret_cast<T*>(a.T);
-    for (int idx = lane; idx < QR_NB * QR_NB; idx += 32) {
-      const int i = idx / QR_NB, c = idx - i * QR_NB;
+    for (int idx = lane; idx < jb * jb; idx += 32) {
+      const int i = idx / jb, c = idx - i * jb;
       T v = N_::zero();
-      if (i <= c && c < jb) v = Z[c * QR_NB + i];
-      Tg[idx] = v;
+      if (i <= c) v = Z[c * QR_NB + i];
+      Tg[i * a.ldt + c] = v;
     }
   }
 
@@ -297,9 +337,11 @@ static inline unsigned blocks_for(int64_t n) {
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+constexpr int QR_NBO = 128;  // outer block: trailing updates and the explicit Q use K = 128 GEMMs
+
 struct QrLayout {
-  int64_t k, ldw, ldv, npanels;
-  size_t off_w, off_v, off_t, off_w1, off_w2, off_sc, total;
+  int64_t k, ldw, ldv, nouter;
+  size_t off_w, off_v, off_t, off_w1, off_w2, off_sc, off_sk, sk_bytes, total;
 };
 
 static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
@@ -308,15 +350,18 @@ static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
   L.k = m < n ? m : n;
   L.ldw = (n + 1) & ~(int64_t)1;
   L.ldv = (L.k + 1) & ~(int64_t)1;
-  L.npanels = (L.k + QR_NB - 1) / QR_NB;
+  L.nouter = (L.k + QR_NBO - 1) / QR_NBO;
   const int64_t wide = (n > L.k ? n : L.k);
   size_t o = 0;
   L.off_w = o;  o += align_up((size_t)m * L.ldw * es);
   L.off_v = o;  o += align_up((size_t)m * L.ldv * es);
-  L.off_t = o;  o += align_up((size_t)L.npanels * QR_NB * QR_NB * es);
-  L.off_w1 = o; o += align_up((size_t)QR_NB * (wide + 2) * es);
-  L.off_w2 = o; o += align_up((size_t)QR_NB * (wide + 2) * es);
+  L.off_t = o;  o += align_up((size_t)L.nouter * QR_NBO * QR_NBO * es);
+  L.off_w1 = o; o += align_up((size_t)QR_NBO * (wide + 2) * es);
+  L.off_w2 = o; o += align_up((size_t)QR_NBO * (wide + 2) * es);
   L.off_sc = o; o += 256;  // [0] amax bits, [1] scale, [2] 1/scale
+  // split-K scratch for the (jb x n2 x m) products: up to 16 partials of a 128 x wide block
+  L.sk_bytes = (m >= 1024) ? align_up((size_t)16 * QR_NBO * wide * es) : 0;
+  L.off_sk = o; o += L.sk_bytes;
   L.total = o;
   return L;
 }
@@ -371,6 +416,12 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
 // scale_mode 0: factor A as it is; 1: factor 2^e A (e from max|A|, so no dot product can overflow) and
 // return R of A itself; 2: as 1 but return R of the SCALED matrix and the factors in scale_out[0..1]
 // (scale, 1/scale) -- used by svd.cu, which folds 1/scale into the singular values.
+//
+// Two-level blocking: columns are factored in inner panels of QR_NB = 32 (cluster kernel), grouped in
+// outer blocks of QR_NBO = 128.  Inside an outer block each panel's reflector is applied to the rest
+// of the block only; the block's 128 x 128 T factor is assembled from the panels' T factors
+// (T12 = -T11 (V1^H V2) T22), and the trailing matrix / the explicit Q see one K = 128 compact-WY
+// update per outer block.  The long-K products V^H A use split-K.
 template <typename T>
 static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws,
                    int scale_mode, double** scale_out, cudaStream_t st) {
@@ -381,6 +432,7 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
   T* Tb = (T*)(base + L.off_t);
   T* W1 = (T*)(base + L.off_w1);
   T* W2 = (T*)(base + L.off_w2);
+  void* sk = L.sk_bytes ? (void*)(base + L.off_sk) : nullptr;
   const int64_t k = L.k;
   double* sc = nullptr;
   if (scale_mode != 0) {
@@ -395,26 +447,57 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
   }
   copy2d_kernel<T><<<blocks_for(m * n), 256, 0, st>>>((const T*)A, lda, W, L.ldw, m, n, sc);
   TNB_LAUNCH_CHECK();
-  // V must be zero outside the panels' own columns/rows it writes (rows above a panel)
+  // V must be zero outside the panels' own columns/rows it writes (rows above a panel); T blocks start zero
   TNB_CUDA_CHECK(cudaMemsetAsync(V, 0, (size_t)m * L.ldv * sizeof(T), st));
-  for (int64_t p = 0; p < L.npanels; ++p) {
-    const int64_t j0 = p * QR_NB;
-    const int jb = (int)((k - j0 < QR_NB) ? (k - j0) : QR_NB);
-    QrPanelArgs a;
-    a.W = W; a.V = V; a.T = Tb + p * QR_NB * QR_NB;
-    a.m = m; a.ldw = L.ldw; a.ldv = L.ldv; a.j0 = j0; a.jb = jb;
-    int rc = launch_panel<T>(a, st);
-    if (rc) return rc;
-    const int64_t n2 = n - j0 - jb, mr = m - j0;
+  TNB_CUDA_CHECK(cudaMemsetAsync(Tb, 0, (size_t)L.nouter * QR_NBO * QR_NBO * sizeof(T), st));
+  int rc;
+  for (int64_t ob = 0; ob < L.nouter; ++ob) {
+    const int64_t j0 = ob * QR_NBO;
+    const int64_t jbo = (k - j0 < QR_NBO) ? (k - j0) : QR_NBO;
+    T* To = Tb + ob * QR_NBO * QR_NBO;  // ld = QR_NBO
+    const T* Vo = V + j0 * L.ldv + j0;
+    const int64_t mro = m - j0;
+    for (int64_t cb = 0; cb < jbo; cb += QR_NB) {
+      const int64_t i0 = j0 + cb;
+      const int jb = (int)((jbo - cb < QR_NB) ? (jbo - cb) : QR_NB);
+      QrPanelArgs a;
+      a.W = W; a.V = V; a.T = To + cb * QR_NBO + cb; a.ldt = QR_NBO;
+      a.m = m; a.ldw = L.ldw; a.ldv = L.ldv; a.j0 = i0; a.jb = jb;
+      rc = launch_panel<T>(a, st);
+      if (rc) return rc;
+      const T* Vp = V + i0 * L.ldv + i0;
+      const T* Tp = To + cb * QR_NBO + cb;
+      const int64_t mri = m - i0;
+      const int64_t nin = jbo - cb - jb;  // columns of this outer block still to the right
+      if (nin > 0) {
+        T* Ain = W + i0 * L.ldw + i0 + jb;
+        // Ain -= Vp Tp^H Vp^H Ain
+        rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, jb, nin, mri, 1, 0, Vp, L.ldv, 0, Ain, L.ldw, 0, 0, 0, W1, nin, 0, 1, sk, L.sk_bytes, st);
+        if (rc) return rc;
+        rc = gemm(dtype, TNB_OP_C, TNB_OP_N, jb, nin, jb, 1, 0, Tp, QR_NBO, 0, W1, nin, 0, 0, 0, W2, nin, 0, 1, st);
+        if (rc) return rc;
+        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, mri, nin, jb, -1, 0, Vp, L.ldv, 0, W2, nin, 0, 1, 0, Ain, L.ldw, 0, 1, st);
+        if (rc) return rc;
+      }
+      if (cb > 0) {
+        // To[0:cb, cb:cb+jb] = -To[0:cb,0:cb] (V1^H V2) Tp,  V1 = Vo[:, 0:cb], V2 = Vo[:, cb:cb+jb]
+        rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, cb, jb, mro, 1, 0, Vo, L.ldv, 0, Vo + cb, L.ldv, 0, 0, 0, W1, jb, 0, 1, sk, L.sk_bytes, st);
+        if (rc) return rc;
+        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, cb, jb, jb, 1, 0, W1, jb, 0, Tp, QR_NBO, 0, 0, 0, W2, jb, 0, 1, st);
+        if (rc) return rc;
+        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, cb, jb, cb, -1, 0, To, QR_NBO, 0, W2, jb, 0, 0, 0, To + cb, QR_NBO, 0, 1, st);
+        if (rc) return rc;
+      }
+    }
+    const int64_t n2 = n - j0 - jbo;
     if (n2 > 0) {
-      const T* Vp = V + j0 * L.ldv + j0;
-      T* A2 = W + j0 * L.ldw + j0 + jb;
-      // W1 = V^H A2 ; W2 = T^H W1 ; A2 -= V W2
-      rc = gemm(dtype, TNB_OP_C, TNB_OP_N, jb, n2, mr, 1, 0, Vp, L.ldv, 0, A2, L.ldw, 0, 0, 0, W1, n2, 0, 1, st);
+      T* A2 = W + j0 * L.ldw + j0 + jbo;
+      // W1 = Vo^H A2 ; W2 = To^H W1 ; A2 -= Vo W2
+      rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, jbo, n2, mro, 1, 0, Vo, L.ldv, 0, A2, L.ldw, 0, 0, 0, W1, n2, 0, 1, sk, L.sk_bytes, st);
       if (rc) return rc;
-      rc = gemm(dtype, TNB_OP_C, TNB_OP_N, jb, n2, jb, 1, 0, a.T, QR_NB, 0, W1, n2, 0, 0, 0, W2, n2, 0, 1, st);
+      rc = gemm(dtype, TNB_OP_C, TNB_OP_N, jbo, n2, jbo, 1, 0, To, QR_NBO, 0, W1, n2, 0, 0, 0, W2, n2, 0, 1, st);
       if (rc) return rc;
-      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, mr, n2, jb, -1, 0, Vp, L.ldv, 0, W2, n2, 0, 1, 0, A2, L.ldw, 0, 1, st);
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, mro, n2, jbo, -1, 0, Vo, L.ldv, 0, W2, n2, 0, 1, 0, A2, L.ldw, 0, 1, st);
       if (rc) return rc;
     }
   }
@@ -426,19 +509,19 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
     T* Qo = (T*)Q;
     eye_kernel<T><<<blocks_for(m * k), 256, 0, st>>>(Qo, m, k, k);
     TNB_LAUNCH_CHECK();
-    for (int64_t p = L.npanels - 1; p >= 0; --p) {
-      const int64_t j0 = p * QR_NB;
-      const int jb = (int)((k - j0 < QR_NB) ? (k - j0) : QR_NB);
-      const int64_t nc = k - j0, mr = m - j0;
-      const T* Vp = V + j0 * L.ldv + j0;
-      const T* Tp = Tb + p * QR_NB * QR_NB;
+    for (int64_t ob = L.nouter - 1; ob >= 0; --ob) {
+      const int64_t j0 = ob * QR_NBO;
+      const int64_t jbo = (k - j0 < QR_NBO) ? (k - j0) : QR_NBO;
+      const int64_t nc = k - j0, mro = m - j0;
+      const T* Vo = V + j0 * L.ldv + j0;
+      const T* To = Tb + ob * QR_NBO * QR_NBO;
       T* Qs = Qo + j0 * k + j0;
-      // Qs := (I - V T V^H) Qs
-      int rc = gemm(dtype, TNB_OP_C, TNB_OP_N, jb, nc, mr, 1, 0, Vp, L.ldv, 0, Qs, k, 0, 0, 0, W1, nc, 0, 1, st);
+      // Qs := (I - Vo To Vo^H) Qs
+      rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, jbo, nc, mro, 1, 0, Vo, L.ldv, 0, Qs, k, 0, 0, 0, W1, nc, 0, 1, sk, L.sk_bytes, st);
       if (rc) return rc;
-      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, jb, nc, jb, 1, 0, Tp, QR_NB, 0, W1, nc, 0, 0, 0, W2, nc, 0, 1, st);
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, jbo, nc, jbo, 1, 0, To, QR_NBO, 0, W1, nc, 0, 0, 0, W2, nc, 0, 1, st);
       if (rc) return rc;
-      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, mr, nc, jb, -1, 0, Vp, L.ldv, 0, W2, nc, 0, 1, 0, Qs, k, 0, 1, st);
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, mro, nc, jbo, -1, 0, Vo, L.ldv, 0, W2, nc, 0, 1, 0, Qs, k, 0, 1, st);
       if (rc) return rc;
     }
   }

@@ -63,7 +63,7 @@ constexpr int JGP = JP + 1;  // pitch of the small matrices in shared memory
 constexpr int MAX_SWEEPS = 60;
 
 struct JacobiFlags {
-  unsigned long long maxoff_bits;  // max off-diagonal cosine of the sweep in flight (double bits)
+  unsigned long long maxoff_bits;  // max squared off-diagonal cosine of the sweep in flight (double bits)
   int converged;
   int sweeps;  // completed sweeps (stops counting once converged)
   int bad;     // a non-finite singular value was produced (NaN / Inf input)
@@ -100,30 +100,39 @@ template <> __device__ __forceinline__ double abs_t<cplx>(cplx v) { return hypot
 // annihilates x_p^H x_q; identity when the pair is already orthogonal to `tol`.
 template <typename T> struct Rot { double c; T sp; double off; };
 
+// `off` is the SQUARED cosine |g|^2 / (alpha beta); `tol2` the squared tolerance.  With
+// tau = (beta - alpha)/2 and h = sqrt(tau^2 + |g|^2):  t = sign(tau) |g| / (|tau| + h),
+// c = 1/sqrt(1 + t^2), sp = c t g/|g| = g * sign(tau) c / (|tau| + h)  -- one sqrt, one
+// reciprocal, one rsqrt, no hypot (X is scaled to unit Frobenius norm, nothing overflows).
 template <typename T>
-__device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol) {
+__device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol2) {
   typedef Num<T> N_;
   Rot<T> r;
   r.c = 1.0; r.sp = N_::zero(); r.off = 0.0;
   const double alpha = N_::real(G[p * JGP + p]), beta = N_::real(G[q * JGP + q]);
   const T gam = G[p * JGP + q];
-  const double ag = abs_t<T>(gam);
-  if (alpha > 0.0 && beta > 0.0 && ag > 0.0) {
-    const double den = sqrt(alpha) * sqrt(beta);
-    if (den > 0.0) {
-      r.off = ag / den;
-      if (r.off > tol) {
-        const double zeta = (beta - alpha) / (2.0 * ag);
-        double t;
-        if (fabs(zeta) > 1e100) t = 0.5 / zeta;
-        else t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        r.c = 1.0 / sqrt(1.0 + t * t);
-        const double s = r.c * t;
-        r.sp = N_::scale(gam, s / ag);
-      }
+  const double ag2 = N_::abs2(gam);
+  const double ab = alpha * beta;
+  if (ab > 0.0 && ag2 > 0.0) {
+    r.off = ag2 / ab;
+    if (r.off > tol2) {
+      const double tau = 0.5 * (beta - alpha);
+      const double h = sqrt(tau * tau + ag2);
+      const double d = 1.0 / (fabs(tau) + h);
+      const double t2 = ag2 * d * d;
+      r.c = rsqrt(1.0 + t2);
+      r.sp = N_::scale(gam, copysign(r.c * d, tau));
     }
   }
   return r;
+}
+
+template <typename T> __device__ __forceinline__ T shfl_t(T v, int src);
+template <> __device__ __forceinline__ double shfl_t<double>(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+template <> __device__ __forceinline__ cplx shfl_t<cplx>(cplx v, int src) {
+  return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
 
 // Shared memory: P[JP][CH+1] | G[JP][JGP] | Gpart[JP][JGP] | W[JP][JGP]
@@ -210,15 +219,20 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   cluster.sync();  // all remote reads done before any CTA moves on (or exits)
 
   // ---- one parallel-ordered Jacobi sweep on G, rotations accumulated in W ------------
-  double maxoff = 0.0;
+  double maxoff = 0.0;  // squared cosine
+  const double tol2 = a.tol * a.tol;
   for (int step = 0; step < JP - 1; ++step) {
     int pa, qa, pb, qb;
     rr_pair(JP, step, ta, pa, qa);
     rr_pair(JP, step, tb, pb, qb);
     if (pa > qa) { const int t = pa; pa = qa; qa = t; }
     if (pb > qb) { const int t = pb; pb = qb; qb = t; }
-    const Rot<T> Ra = make_rot<T>(G, pa, qa, a.tol);
-    const Rot<T> Rb = make_rot<T>(G, pb, qb, a.tol);
+    // every thread builds the rotation of pair tb = lane & 15; the one of pair ta comes from lane ta
+    const Rot<T> Rb = make_rot<T>(G, pb, qb, tol2);
+    Rot<T> Ra;
+    Ra.c = __shfl_sync(0xffffffffu, Rb.c, ta);
+    Ra.sp = shfl_t<T>(Rb.sp, ta);
+    Ra.off = Rb.off;  // only used when ta == tb
     const T b00 = G[pa * JGP + pb], b01 = G[pa * JGP + qb], b10 = G[qa * JGP + pb], b11 = G[qa * JGP + qb];
     const T w00 = W[(2 * ta) * JGP + pb], w01 = W[(2 * ta) * JGP + qb];
     const T w10 = W[(2 * ta + 1) * JGP + pb], w11 = W[(2 * ta + 1) * JGP + qb];
@@ -297,9 +311,11 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
 
 __global__ void jacobi_finish_sweep_kernel(JacobiFlags* f, double tol) {
   if (f->converged) return;
-  const double off = __longlong_as_double((long long)f->maxoff_bits);
+  const double off2 = __longlong_as_double((long long)f->maxoff_bits);  // squared cosine
   f->sweeps += 1;
-  if (off <= tol) f->converged = 1;
+  // Cyclic Jacobi converges quadratically: a sweep that STARTED with every cosine below 1e-10 leaves
+  // them far below tol, so the confirming sweep is skipped (it would only re-measure).
+  if (off2 <= tol * tol || off2 <= 1e-20) f->converged = 1;
   f->maxoff_bits = 0ull;
 }
 
