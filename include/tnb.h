@@ -149,6 +149,13 @@ size_t tnb_svd_workspace(int dtype, int64_t m, int64_t n);
 int tnb_svd(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
             void* U, double* S, void* Vh, void* ws, size_t ws_bytes, int* sweeps_out, void* stream);
 
+/* Projection form used by the MPS sweeps (onedim_core.py:317-351): U and S as above, and
+ * P = U^H A = diag(S) Vh (k x n) -- the product the sweep absorbs into the next site.  V is never
+ * accumulated (one third fewer Jacobi flops); the rows of P carry an absolute error of eps |A|.
+ * Same workspace as tnb_svd. */
+int tnb_svd_project(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
+                    void* U, double* S, void* P, void* ws, size_t ws_bytes, int* sweeps_out, void* stream);
+
 /* ---- truncation rule on device ---------------------------------------------
  * kept = #{ i < (chi>0 ? chi : n) : s[i] > bar }, bar = threshold (relative
  * == 0, absolute) or threshold*s[0] (relative == 1, tensor.py:1150); relative

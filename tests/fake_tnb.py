@@ -219,6 +219,31 @@ class FakeLib:
         return 0
 
 
+def _svd_project(self, code, m, n, A, lda, U, S, P, ws, nbytes, sweeps, stream):
+    self._count("svd_project")
+    a = _mat(_val(A), m, n, lda, _dt(code))
+    u, s, vh = np.linalg.svd(a, full_matrices=False)
+    k = min(m, n)
+    _flat(_val(U), m * k, a.dtype)[:] = u.ravel()
+    _flat(_val(S), k, np.float64)[:] = s
+    if _val(P):
+        _flat(_val(P), k * n, a.dtype)[:] = (s[:, None] * vh).ravel()
+    return 0
+
+
+def _fill_uniform(self, out, n, key, offset, stream):
+    from tncontract_b200.batch import host_uniform
+    self._count("fill_uniform")
+    k = key.value if hasattr(key, "value") else key
+    o = offset.value if hasattr(offset, "value") else offset
+    _flat(_val(out), n, np.float64)[:] = host_uniform(n, k, o)
+    return 0
+
+
+FakeLib.tnb_svd_project = _svd_project
+FakeLib.tnb_fill_uniform = _fill_uniform
+
+
 def install(monkeypatch):
     """Route tncontract_b200 to FakeLib + host torch buffers (one test only)."""
     import torch

@@ -210,14 +210,15 @@ def test_singular_values_per_bond(backend):
     from tncontract_b200 import devarray as dv
     g = Golden("mps_real")
     seen = []
-    orig = dv.svd
+    orig, orig_p = dv.svd, dv.svd_project
 
-    def spy(a):
-        out = orig(a)
+    def spy(a, fn=None):
+        out = (fn or orig)(a)
         seen.append(np.asarray(out[1]))
         return out
 
     dv.svd = spy
+    dv.svd_project = lambda a: spy(a, orig_p)   # the sweeps use the projection form (U, s, diag(s) Vh)
     try:
         a = to_chain(g, "psi"); a.left_canonise()
         assert len(seen) == g.meta["lc_svd.nsvd"]
@@ -231,7 +232,7 @@ def test_singular_values_per_bond(backend):
             ref = g.scalar("comp8.s%d" % i)
             assert s.shape == ref.shape and np.max(np.abs(s - ref)) <= TOL * ref[0]
     finally:
-        dv.svd = orig
+        dv.svd, dv.svd_project = orig, orig_p
 
 
 def test_mps_complex_apply_compress_energy(backend):

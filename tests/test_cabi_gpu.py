@@ -319,3 +319,34 @@ def test_elementwise(cplx):
             want = int(np.sum(lim / sv[0] > thr))
         assert kept == want and s0 == sv[0]
         assert np.array_equal(np.asarray(scaled), sv / sv[0])
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_svd_project(cplx):
+    """tnb_svd_project: U, S and P = U^H A = diag(S) Vh, V never accumulated."""
+    torch, _lib, dv = _mods()
+    rng = np.random.default_rng(8)
+    for m, n in [(1, 1), (6, 1), (1, 6), (20, 12), (12, 20), (64, 64), (96, 200), (200, 96), (256, 384)]:
+        a = rnd(rng, (m, n), cplx)
+        u, s, p = dv.svd_project(dv.DevArray.from_host(a))
+        u, s, p = np.asarray(u), np.asarray(s), np.asarray(p)
+        k = min(m, n)
+        assert u.shape == (m, k) and s.shape == (k,) and p.shape == (k, n)
+        sref = np.linalg.svd(a, compute_uv=False)
+        assert np.max(np.abs(s - sref)) <= 1e-12 * sref[0]
+        assert np.linalg.norm(u.conj().T @ u - np.eye(k)) < 1e-11 * max(1, k)
+        assert rel(p, u.conj().T @ a) < 1e-12
+        assert rel(u @ p, a) < 1e-11
+        # rows of P are orthogonal with norms S
+        g = p @ p.conj().T
+        assert np.linalg.norm(g - np.diag(s ** 2)) < 1e-11 * sref[0] ** 2 * max(1, k)
+    # graded spectrum: small singular values keep relative accuracy without V
+    a = rnd(rng, (90, 140), cplx) * np.logspace(0, -10, 140)[None, :]
+    u, s, p = dv.svd_project(dv.DevArray.from_host(a))
+    sref = np.linalg.svd(a, compute_uv=False)
+    assert np.max(np.abs(np.asarray(s) - sref) / sref) < 1e-9
+    b = (rnd(rng, (150, 70), cplx) * np.logspace(0, -10, 70)[None, :])
+    u, s, p = dv.svd_project(dv.DevArray.from_host(b))
+    sref = np.linalg.svd(b, compute_uv=False)
+    assert np.max(np.abs(np.asarray(s) - sref) / sref) < 1e-9
+    assert np.linalg.norm(np.asarray(u).conj().T @ np.asarray(u) - np.eye(70)) < 1e-10

@@ -61,6 +61,7 @@ SIGNATURES = {
     "tnb_qr": (_c.c_int, [_c.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "tnb_svd_workspace": (_sz, [_c.c_int, _i64, _i64]),
     "tnb_svd": (_c.c_int, [_c.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _pi32, _vp]),
+    "tnb_svd_project": (_c.c_int, [_c.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _pi32, _vp]),
     "tnb_truncation_count": (_c.c_int, [_vp, _i64, _i64, _dbl, _c.c_int, _vp, _vp, _vp]),
 }
 

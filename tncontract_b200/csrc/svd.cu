@@ -467,11 +467,11 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
   a.tol = sqrt((double)(L > 1 ? L : 1)) * 2.220446049250313e-16;
   const int ch_max = cplx ? 256 : 512;
   int CH = 32;
-  const int64_t longest = L > n ? L : n;
+  const int64_t longest = (L > n || !Vt) ? L : n;
   while (CH < ch_max && CH < longest) CH *= 2;
   a.CH = CH;
   a.nx = (int)((L + CH - 1) / CH);
-  a.nv = (int)((n + CH - 1) / CH);
+  a.nv = Vt ? (int)((n + CH - 1) / CH) : 0;
   int S = 1;
   while (S * 2 <= 8 && S * 2 <= a.nx + a.nv && npairs * S * 2 <= sm_count()) S *= 2;
   a.S = S;
@@ -503,9 +503,14 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
   return h.converged ? 0 : TNB_E_NOCONV;
 }
 
+// mode 0: U, S, Vh (V accumulated through the Jacobi rotations).
+// mode 1: U, S and P = U^H A = diag(S) Vh -- what the MPS sweeps absorb into the next site
+//         (onedim_core.py:347-349 contracts V and then S into it).  V is never formed: Jacobi then
+//         runs on the triangular factor only (one third fewer flops, half the traffic) and P is one
+//         DMMA GEMM on the original A, accurate to eps |A| whatever the size of the singular value.
 template <typename T>
 static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* U, double* S, void* Vh,
-                    void* ws, int* sweeps_out, cudaStream_t st) {
+                    void* ws, int* sweeps_out, int mode, cudaStream_t st) {
   const SvdLayout L = svd_layout(dtype, m, n);
   char* base = (char*)ws;
   const int64_t k = L.k;
@@ -520,6 +525,7 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   double* nrm = (double*)(base + L.off_nrm);
   void* qr_ws = base + L.off_qr;
   const bool wide = m < n;
+  const bool proj = (mode == 1);
   int rc;
   double* qscale = nullptr;  // device: [0] power-of-two scale applied before the QR, [1] its inverse
   if (!wide) {
@@ -533,9 +539,14 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     rc = qr(dtype, n, m, AH, m, Q, R, qr_ws, 2, &qscale, st);
     if (rc) return rc;
   }
-  {  // Xt = conj(R): row j of Xt is column j of X = R^H
-    const int64_t sh[2] = {k, k}, is[2] = {k, 1};
-    rc = permute_view(dtype, R, 2, sh, is, Xt, 1.0, 0.0, 1, st);
+  // Jacobi orthogonalises the columns of X, stored as rows of Xt:
+  //   X = R^H (Xt = conj(R)) -- except for a tall matrix in projection mode, where the LEFT vectors
+  //   are wanted from the column space of R itself: X = R (Xt = R^T).
+  const bool x_is_r = proj && !wide;
+  {
+    const int64_t sh[2] = {k, k};
+    const int64_t is_conj[2] = {k, 1}, is_tr[2] = {1, k};
+    rc = permute_view(dtype, R, 2, sh, x_is_r ? is_tr : is_conj, Xt, 1.0, 0.0, x_is_r ? 0 : 1, st);
     if (rc) return rc;
   }
   {  // Jacobi works on Gram matrices (squared magnitudes): bring X to unit Frobenius norm first
@@ -546,35 +557,56 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     unit_scale_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k * k, nrm, nrm + 1, qscale);
     TNB_LAUNCH_CHECK();
   }
-  eye_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Vt, k);
-  TNB_LAUNCH_CHECK();
-  rc = jacobi<T>(Xt, k, k, Vt, k, flags, sweeps_out, st);
+  if (!proj) {
+    eye_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Vt, k);
+    TNB_LAUNCH_CHECK();
+  }
+  rc = jacobi<T>(Xt, k, k, proj ? (T*)nullptr : Vt, k, flags, sweeps_out, st);
   if (rc) return rc;
   row_norm_kernel<T><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(Xt, k, k, k, sig);
   TNB_LAUNCH_CHECK();
   rank_kernel<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(sig, k, perm, S, nrm + 1, flags);
   TNB_LAUNCH_CHECK();
-  // Vs[j, :] = Vt[perm[j], :]  (column j of the sorted V, as a row)
-  gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Vt, k, perm, S, Vs, k, k, k, 0, 0, 0);
-  TNB_LAUNCH_CHECK();
-  if (!wide) {
-    // A = Q R, R = V Sigma Ux^H:  U = Q V,  Vh = Ux^H = conj(Y^T) / sigma
-    if (Vh) {
-      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, (T*)Vh, n, k, k, 1, 1, 0);
-      TNB_LAUNCH_CHECK();
+  if (!proj) {
+    // Vs[j, :] = Vt[perm[j], :]  (column j of the sorted V, as a row)
+    gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Vt, k, perm, S, Vs, k, k, k, 0, 0, 0);
+    TNB_LAUNCH_CHECK();
+    if (!wide) {
+      // A = Q R, R = V Sigma Ux^H:  U = Q V,  Vh = Ux^H = conj(Y^T) / sigma
+      if (Vh) {
+        gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, (T*)Vh, n, k, k, 1, 1, 0);
+        TNB_LAUNCH_CHECK();
+      }
+      if (U) {
+        rc = gemm(dtype, TNB_OP_N, TNB_OP_T, m, k, k, 1, 0, Q, k, 0, Vs, k, 0, 0, 0, U, k, 0, 1, st);
+        if (rc) return rc;
+      }
+    } else {
+      // A = R^H Q^H = Ux Sigma (Q V)^H:  U = Y / sigma,  Vh = conj(Vs) Q^H
+      if (U) {
+        gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, (T*)U, k, k, k, 0, 1, 1);
+        TNB_LAUNCH_CHECK();
+      }
+      if (Vh) {
+        rc = gemm(dtype, TNB_OP_J, TNB_OP_C, k, n, k, 1, 0, Vs, k, 0, Q, k, 0, 0, 0, Vh, n, 0, 1, st);
+        if (rc) return rc;
+      }
     }
-    if (U) {
+  } else {
+    if (!U) return TNB_E_ARG;
+    if (wide) {
+      // A = R^H Q^H, R^H V = Y:  U = Y / sigma (left vectors of R^H are those of A)
+      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, (T*)U, k, k, k, 0, 1, 1);
+      TNB_LAUNCH_CHECK();
+    } else {
+      // A = Q R, R V = Y = Ur Sigma:  U = Q Ur, with Ur^T = sorted rows of Yt / sigma (kept in Vs)
+      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, Vs, k, k, k, 0, 1, 0);
+      TNB_LAUNCH_CHECK();
       rc = gemm(dtype, TNB_OP_N, TNB_OP_T, m, k, k, 1, 0, Q, k, 0, Vs, k, 0, 0, 0, U, k, 0, 1, st);
       if (rc) return rc;
     }
-  } else {
-    // A = R^H Q^H = Ux Sigma (Q V)^H:  U = Y / sigma,  Vh = conj(Vs) Q^H
-    if (U) {
-      gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, (T*)U, k, k, k, 0, 1, 1);
-      TNB_LAUNCH_CHECK();
-    }
-    if (Vh) {
-      rc = gemm(dtype, TNB_OP_J, TNB_OP_C, k, n, k, 1, 0, Vs, k, 0, Q, k, 0, 0, 0, Vh, n, 0, 1, st);
+    if (Vh) {  // P = U^H A  (k x n)
+      rc = gemm(dtype, TNB_OP_C, TNB_OP_N, k, n, m, 1, 0, U, k, 0, A, lda, 0, 0, 0, Vh, n, 0, 1, st);
       if (rc) return rc;
     }
   }
@@ -599,6 +631,18 @@ extern "C" int tnb_svd(int dtype, int64_t m, int64_t n, const void* A, int64_t l
   if (m == 0 || n == 0) return 0;
   if (!A || !S || !ws) return TNB_E_ARG;
   if (ws_bytes < tnb::svd_layout(dtype, m, n).total) return TNB_E_WORKSPACE;
-  if (dtype == TNB_F64) return tnb::svd_impl<double>(dtype, m, n, A, lda, U, S, Vh, ws, sweeps_out, (cudaStream_t)stream);
-  return tnb::svd_impl<tnb::cplx>(dtype, m, n, A, lda, U, S, Vh, ws, sweeps_out, (cudaStream_t)stream);
+  if (dtype == TNB_F64) return tnb::svd_impl<double>(dtype, m, n, A, lda, U, S, Vh, ws, sweeps_out, 0, (cudaStream_t)stream);
+  return tnb::svd_impl<tnb::cplx>(dtype, m, n, A, lda, U, S, Vh, ws, sweeps_out, 0, (cudaStream_t)stream);
+}
+
+extern "C" int tnb_svd_project(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* U, double* S, void* P,
+                               void* ws, size_t ws_bytes, int* sweeps_out, void* stream) {
+  if (dtype != TNB_F64 && dtype != TNB_C128) return TNB_E_ARG;
+  if (m < 0 || n < 0 || lda < n) return TNB_E_ARG;
+  if (sweeps_out) *sweeps_out = 0;
+  if (m == 0 || n == 0) return 0;
+  if (!A || !S || !U || !ws) return TNB_E_ARG;
+  if (ws_bytes < tnb::svd_layout(dtype, m, n).total) return TNB_E_WORKSPACE;
+  if (dtype == TNB_F64) return tnb::svd_impl<double>(dtype, m, n, A, lda, U, S, P, ws, sweeps_out, 1, (cudaStream_t)stream);
+  return tnb::svd_impl<tnb::cplx>(dtype, m, n, A, lda, U, S, P, ws, sweeps_out, 1, (cudaStream_t)stream);
 }

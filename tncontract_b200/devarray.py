@@ -395,6 +395,27 @@ def svd(a):
     return DevArray(u), DevArray(s), DevArray(vh)
 
 
+def svd_project(a):
+    """(u, s, p) with p = u^H a = diag(s) vh: the form the MPS sweeps consume (tnb_svd_project)."""
+    global last_svd_sweeps
+    m, n = a.shape
+    k = min(m, n)
+    a, lda = _as_matrix(a)
+    u, s, p = _empty((m, k), a.dtype), _empty((k,), np.float64), _empty((k, n), a.dtype)
+    if m * n == 0:
+        return DevArray(u), DevArray(s), DevArray(p)
+    lib = _lib.load()
+    code = _lib.dtype_code(a.dtype)
+    need = lib.tnb_svd_workspace(code, m, n)
+    ws_t, ws = workspace(need)
+    sweeps = ctypes.c_int32(0)
+    _lib.check(lib.tnb_svd_project(code, m, n, ctypes.c_void_p(a.ptr), lda, ctypes.c_void_p(u.data_ptr()),
+                                   ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(p.data_ptr()), ws, need,
+                                   ctypes.byref(sweeps), stream_ptr()))
+    last_svd_sweeps = sweeps.value
+    return DevArray(u), DevArray(s), DevArray(p)
+
+
 def truncation(s, chi, threshold, relative):
     """Kept-rank rule on device; returns (kept:int, s0:float, s_scaled DevArray).
     One 16-byte read-back (the kept rank fixes the next tensor's shape)."""

@@ -218,7 +218,9 @@ class MatrixProductState(_PhysLabelMixin, OneDimensionalTensorNetwork):
                 nxt.replace_label(tag + "out", self.left_label)
                 self[i + 1] = nxt
                 continue
-            U, s, V = tsr._svd_parts(self[i], rows, tag)
+            # U, s and P = diag(s) V in one call: the reference contracts V and then diag(s / s0) into
+            # the next site (:347-349); that product is (U^H A) / s0, so V itself is never needed
+            U, s, P = tsr._svd_parts(self[i], rows, tag, project=True)
             # s/s0 > threshold, then [:chi] (:333-339), evaluated on the device
             kept, s0, s_rel = dv.truncation(s, chi, threshold, relative=2)
             if s0 == 0.0:
@@ -226,11 +228,11 @@ class MatrixProductState(_PhysLabelMixin, OneDimensionalTensorNetwork):
                 return
             scale = scale * s0
             U.data = U.data[:, :, 0:kept]
-            V.data = V.data[0:kept]
+            P.data = P.data[0:kept]
+            P.data *= 1.0 / s0
             U.replace_label(tag + "in", self.right_label)
             self[i] = U
-            nxt = tsr.contract(V, self[i + 1], self.right_label, self.left_label)
-            dv.diag_scale_rows(nxt.data, s_rel[0:kept])  # == contract(diag(s), nxt) of :349
+            nxt = tsr.contract(P, self[i + 1], self.right_label, self.left_label)
             nxt.replace_label(tag + "out", self.left_label)
             self[i + 1] = nxt
             if i == end - 1:

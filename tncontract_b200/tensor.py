@@ -449,8 +449,9 @@ def matrix_to_tensor(matrix, shape, labels=None):
 
 
 # ---- factorisations ---------------------------------------------------------------------------
-def _svd_parts(tensor, row_labels, svd_label):
-    """Matricise + tnb_svd; returns U, s (device vector), V tensors."""
+def _svd_parts(tensor, row_labels, svd_label, project=False):
+    """Matricise + tnb_svd; returns U, s (device vector), V tensors.  With ``project`` the third
+    tensor is P = diag(s) V (tnb_svd_project), the product the MPS sweeps absorb into the next site."""
     row_labels = list(row_labels)
     order, labels = _rows_first(tensor, row_labels)
     data = tensor.data.transpose(order)
@@ -459,7 +460,7 @@ def _svd_parts(tensor, row_labels, svd_label):
     m = _prod(shape[:nr])
     n = int(_prod(shape) / m) if m else 0
     col_labels = [l for l in labels if l not in row_labels]
-    u, s, vh = dv.svd(data.reshape((m, n)))
+    u, s, vh = (dv.svd_project if project else dv.svd)(data.reshape((m, n)))
     k = s.size
     U = Tensor._wrap(u.reshape(tuple(shape[:nr]) + (k,)), row_labels + [svd_label + "in"])
     V = Tensor._wrap(vh.reshape((k,) + tuple(shape[nr:])), [svd_label + "out"] + col_labels)
