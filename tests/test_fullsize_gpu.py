@@ -79,14 +79,17 @@ def test_cfg3_bulk_site_factorisations(shape):
         assert np.max(np.abs(s_h - sref)) < 1e-10 * sref[0]
 
 
-def test_cfg3_apply_compress_energy_reduced_chain():
+@pytest.mark.parametrize("n", [18, 22])
+def test_cfg3_apply_compress_energy_reduced_chain(n):
     """cfg 3 with the full bond dimension (chi=512, D=3, complex128) on a shorter
-    chain (N=22 reaches the chi-capped bulk): energy through the MPO, apply +
-    svd_compress, linearity of the apply, and the variational bound."""
+    chain: energy through the MPO, apply + svd_compress, linearity of the apply,
+    and the variational bound.  N=18: every bond of H|psi> has Schmidt rank
+    <= 2^9 = chi, so the compression must be lossless; N=22 reaches the chi-capped
+    bulk (1024 x 1536 SVDs truncated to 512), where it is a proper projection."""
     import bench
     tn = _tn()
     od = tn.onedim
-    n, d, chi = 22, 2, 512
+    d, chi = 2, 512
     sites = bench.make_host_sites(n, d, chi, seed=2)
     W = bench.tfi_w()
     ws = [W[2] if i == 0 else (W[:, 0] if i == n - 1 else W) for i in range(n)]
@@ -109,10 +112,17 @@ def test_cfg3_apply_compress_energy_reduced_chain():
     assert max(c.bonddims()) == chi
     assert c.bonddims() == [min(chi, 2 ** i, 2 ** (n - i)) for i in range(n + 1)]
     assert c.check_canonical_form(threshold=1e-8, print_output=False) == (0, 0)
-    # H psi has Schmidt rank <= 2^min(i, n-i) <= chi on every bond here, so compression is lossless
-    assert abs(od.inner_product_mps(phi, c) - h2) < 1e-10 * abs(h2)
-    assert abs(c.norm() ** 2 - h2.real) < 1e-10 * abs(h2)
-    assert abs(od.inner_product_mps(psi, c) - e) < 1e-10 * max(abs(e), 1.0)
+    pc = od.inner_product_mps(phi, c)
+    if n == 18:
+        # Schmidt rank <= 2^min(i, n-i) <= chi on every bond: lossless
+        assert abs(pc - h2) < 1e-10 * abs(h2)
+        assert abs(c.norm() ** 2 - h2.real) < 1e-10 * abs(h2)
+        assert abs(od.inner_product_mps(psi, c) - e) < 1e-10 * max(abs(e), 1.0)
+    else:
+        # truncating: c = P phi with P (nearly) an orthogonal projector: <phi|c> = |c|^2 <= |phi|^2
+        assert c.norm() ** 2 <= h2.real * (1 + 1e-12)
+        assert abs(pc - c.norm() ** 2) < 1e-6 * abs(h2) and abs(pc.imag) < 1e-9 * abs(h2)
+        assert c.norm() ** 2 > 0.5 * h2.real
 
 
 def test_cfg4_one_network():
@@ -163,4 +173,4 @@ def test_cfg5_peps_boundary_reduced():
     assert v32 > 0 and v81 > 0                              # <psi|psi>
     assert abs(v32 - v81) < 2e-2 * v81
     mirrored = net.fliplr().mps_contract(81)
-    assert abs(np.float64(mirrored.data) - v81) < 1e-9 * v81
+    assert abs(np.float64(mirrored.data) - v81) < 1e-3 * v81   # chi=81 is itself approximate on 6x6

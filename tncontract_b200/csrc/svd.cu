@@ -59,7 +59,8 @@ int permute_view(int dtype, const void* in, int rank, const int64_t* oshape, con
 constexpr int JB = 16;       // Jacobi block width (columns)
 constexpr int JP = 2 * JB;   // columns in a block pair
 constexpr int JT = 256;      // threads per CTA = (JP/2)^2: thread (a, b) owns a 2x2 block
-constexpr int JGP = JP + 1;  // pitch of the small matrices in shared memory
+constexpr int JGP = JP + 4;  // pitch of the small matrices in shared memory (= 4 mod 8: conflict-free DMMA fragments)
+constexpr int JPAD = 4;      // panel pitch = CH + JPAD for the same reason
 constexpr int MAX_SWEEPS = 60;
 
 struct JacobiFlags {
@@ -135,7 +136,7 @@ template <> __device__ __forceinline__ cplx shfl_t<cplx>(cplx v, int src) {
   return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
 
-// Shared memory: P[JP][CH+1] | G[JP][JGP] | Gpart[JP][JGP] | W[JP][JGP]
+// Shared memory: P[JP][CH+JPAD] | G[JP][JGP] | Gpart[JP][JGP] | W[JP][JGP]
 template <typename T>
 __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   typedef Num<T> N_;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   if (bI > bJ) { const int t = bI; bI = bJ; bJ = t; }
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int CH = a.CH, pitch = CH + 1;
+  const int CH = a.CH, pitch = CH + JPAD;
   T* P = reinterpret_cast<T*>(smem_raw);
   T* G = P + (size_t)JP * pitch;
   T* Gpart = G + JP * JGP;
@@ -179,32 +180,56 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     }
   };
 
-  // ---- partial Gram matrix of this CTA's Xt chunks -----------------------------------
-  T acc[2][2];
-  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = N_::zero();
+  // ---- partial Gram matrix of this CTA's Xt chunks on the FP64 tensor pipe (DMMA.8x8x4) ----------
+  // G[p][q] = sum_c conj(P[p][c]) P[q][c]: 4 x 4 tiles of 8 x 8, two per warp; both fragments are rows of P
+  // with c (= k) contiguous, lane (gq, tq) holds element [row0 + gq][k0 + tq].
+  constexpr bool CPLX = (sizeof(T) == 16);
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  double g[2][CPLX ? 4 : 2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int r = 0; r < (CPLX ? 4 : 2); ++r) g[j][r] = 0.0;
+  const int gm = warp >> 1, gn0 = (warp & 1) * 2;
   int resident = -1;
-  for (int g = crank; g < a.nx; g += S) {
+  for (int gch = crank; gch < a.nx; gch += S) {
     __syncthreads();
-    load_chunk(g);
+    load_chunk(gch);
     __syncthreads();
-    resident = g;
-    const T* ra0 = P + (2 * ta) * pitch;
-    const T* ra1 = ra0 + pitch;
-    const T* rb0 = P + (2 * tb) * pitch;
-    const T* rb1 = rb0 + pitch;
+    resident = gch;
+    const T* pa = P + (gm * 8 + gq) * pitch + tq;
+    const T* pb0 = P + (gn0 * 8 + gq) * pitch + tq;
+    const T* pb1 = pb0 + 8 * pitch;
 #pragma unroll 4
-    for (int c = 0; c < CH; ++c) {
-      const T x0 = ra0[c], x1 = ra1[c], y0 = rb0[c], y1 = rb1[c];
-      acc[0][0] = N_::fma_conj(x0, y0, acc[0][0]);
-      acc[0][1] = N_::fma_conj(x0, y1, acc[0][1]);
-      acc[1][0] = N_::fma_conj(x1, y0, acc[1][0]);
-      acc[1][1] = N_::fma_conj(x1, y1, acc[1][1]);
+    for (int k0 = 0; k0 < CH; k0 += 4) {
+      const T av = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
+      if constexpr (CPLX) {
+        const double nay = -av.y;
+        dmma884(g[0][0], g[0][1], av.x, b0.x);
+        dmma884(g[0][2], g[0][3], av.x, b0.y);
+        dmma884(g[1][0], g[1][1], av.x, b1.x);
+        dmma884(g[1][2], g[1][3], av.x, b1.y);
+        dmma884(g[0][0], g[0][1], av.y, b0.y);
+        dmma884(g[0][2], g[0][3], nay, b0.x);
+        dmma884(g[1][0], g[1][1], av.y, b1.y);
+        dmma884(g[1][2], g[1][3], nay, b1.x);
+      } else {
+        dmma884(g[0][0], g[0][1], av, b0);
+        dmma884(g[1][0], g[1][1], av, b1);
+      }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) Gpart[(2 * ta + i) * JGP + 2 * tb + j] = acc[i][j];
+  for (int j = 0; j < 2; ++j) {
+    const int r = gm * 8 + gq, c = (gn0 + j) * 8 + 2 * tq;
+    if constexpr (CPLX) {
+      Gpart[r * JGP + c] = make_double2(g[j][0], g[j][2]);
+      Gpart[r * JGP + c + 1] = make_double2(g[j][1], g[j][3]);
+    } else {
+      Gpart[r * JGP + c] = g[j][0];
+      Gpart[r * JGP + c + 1] = g[j][1];
+    }
+  }
   for (int idx = tid; idx < JP * JP; idx += JT) {
     const int i = idx / JP, j = idx - i * JP;
     W[i * JGP + j] = (i == j) ? N_::one() : N_::zero();
@@ -274,38 +299,75 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
       atomicMax(&a.flags->maxoff_bits, (unsigned long long)__double_as_longlong(maxoff));
   }
 
-  // ---- rows_new[q] = sum_p W[p][q] rows[p] on every chunk of this CTA --------------------
-  auto apply_chunk = [&](int g) {
+  // ---- rows_new[q] = sum_p W[p][q] rows[p] on every chunk of this CTA, again on DMMA: per warp a
+  //      32 (q) x 32 (c) x 32 (p) product; A[m = q][k = p] = W[p][q], B[k = p][n = c] = P[p][c].
+  //      A warp reads and rewrites only its own 32 columns of P, so the result goes back into P in
+  //      place and is stored to global memory with full 512-byte row segments.
+  auto apply_chunk = [&](int gch) {
     T* base; int64_t ld, c0; int len;
-    chunk_geom(g, base, ld, c0, len);
-    for (int c = tid; c < len; c += JT) {
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        T out[JB];
+    chunk_geom(gch, base, ld, c0, len);
+    for (int cw = warp * 32; cw < CH; cw += 8 * 32) {
+      if (cw >= len) break;
+      double acc[4][4][CPLX ? 4 : 2];
 #pragma unroll
-        for (int q = 0; q < JB; ++q) out[q] = N_::zero();
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[mt][nt][r] = 0.0;
 #pragma unroll 2
-        for (int p = 0; p < JP; ++p) {
-          const T x = P[p * pitch + c];
-          const T* wrow = W + p * JGP + half * JB;
+      for (int k0 = 0; k0 < JP; k0 += 4) {
+        T av[4], bv[4];
 #pragma unroll
-          for (int q = 0; q < JB; ++q) out[q] = N_::fma(wrow[q], x, out[q]);
+        for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JGP + mt * 8 + gq];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bv[nt] = P[(k0 + tq) * pitch + cw + nt * 8 + gq];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            if constexpr (CPLX) {
+              dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt].x, bv[nt].x);
+              dmma884(acc[mt][nt][2], acc[mt][nt][3], av[mt].x, bv[nt].y);
+              dmma884(acc[mt][nt][0], acc[mt][nt][1], -av[mt].y, bv[nt].y);
+              dmma884(acc[mt][nt][2], acc[mt][nt][3], av[mt].y, bv[nt].x);
+            } else {
+              dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
+            }
+          }
         }
+      }
+      __syncwarp();
 #pragma unroll
-        for (int q = 0; q < JB; ++q) {
-          const int64_t r = grow(half * JB + q);
-          if (r >= 0) base[r * ld + c0 + c] = out[q];
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          T* dst = P + (mt * 8 + gq) * pitch + cw + nt * 8 + 2 * tq;
+          if constexpr (CPLX) {
+            dst[0] = make_double2(acc[mt][nt][0], acc[mt][nt][2]);
+            dst[1] = make_double2(acc[mt][nt][1], acc[mt][nt][3]);
+          } else {
+            dst[0] = acc[mt][nt][0];
+            dst[1] = acc[mt][nt][1];
+          }
+        }
+      __syncwarp();
+      if (cw + lane < len) {
+#pragma unroll 4
+        for (int q = 0; q < JP; ++q) {
+          const int64_t r = grow(q);
+          if (r >= 0) base[r * ld + c0 + cw + lane] = P[q * pitch + cw + lane];
         }
       }
     }
   };
   if (resident >= 0) apply_chunk(resident);
-  for (int g = crank; g < a.nx + a.nv; g += S) {
-    if (g == resident) continue;
+  for (int gch = crank; gch < a.nx + a.nv; gch += S) {
+    if (gch == resident) continue;
     __syncthreads();
-    load_chunk(g);
+    load_chunk(gch);
     __syncthreads();
-    apply_chunk(g);
+    apply_chunk(gch);
   }
 }
 
@@ -475,7 +537,7 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
   int S = 1;
   while (S * 2 <= 8 && S * 2 <= a.nx + a.nv && npairs * S * 2 <= sm_count()) S *= 2;
   a.S = S;
-  const size_t smem = ((size_t)JP * (CH + 1) + 3 * (size_t)JP * JGP) * sizeof(T);
+  const size_t smem = ((size_t)JP * (CH + JPAD) + 3 * (size_t)JP * JGP) * sizeof(T);
   TNB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(JacobiFlags), st));
   int queued = 0;
   JacobiFlags h;
