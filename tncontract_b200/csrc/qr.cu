@@ -200,22 +200,65 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
   }
   __syncthreads();
 
-  // ---- T factor: Z = strictly-upper part of V^H V, reduced over the cluster --------------------
-  for (int idx = warp; idx < jb * jb; idx += QR_WARPS) {
-    const int i = idx / jb, c = idx - i * jb;
-    if (i >= c) { if (lane == 0) Z[i * QR_NB + c] = N_::zero(); continue; }
-    // v_i^H v_c over rows r > c (both below their diagonals), plus row c where v_c = 1
-    T acc = N_::zero();
-    int lo = (int)(c + 1 - r_lo);
-    if (lo < 0) lo = 0;
-    const T* vi = P + i * a.pitch;
-    const T* vc = P + c * a.pitch;
-    for (int r = lo + lane; r < nrows; r += 32) acc = N_::fma_conj(vi[r], vc[r], acc);
-    acc = warp_sum_t<T>(acc);
-    if (lane == 0) {
-      const int cl = (int)(c - r_lo);
-      if (cl >= 0 && cl < nrows) acc = N_::add(acc, N_::conj(vi[cl]));
-      Z[i * QR_NB + c] = acc;
+  // ---- R goes out; P becomes the explicit V (zeros above the diagonal, ones on it, zero pad rows) ----
+  const int K4 = (nrows + 3) & ~3;
+  for (int i = tid; i < nrows * jb; i += QR_THREADS) {
+    const int r = i / jb, c = i - r * jb;
+    const int64_t pr = r_lo + r;  // panel row
+    if (pr <= c) {
+      Wg[(a.j0 + pr) * a.ldw + a.j0 + c] = P[c * a.pitch + r];
+      P[c * a.pitch + r] = (pr == c) ? N_::one() : N_::zero();
+    }
+  }
+  for (int i = tid; i < (K4 - nrows) * QR_NB; i += QR_THREADS) {
+    const int c = i / (K4 - nrows), r = nrows + (i - c * (K4 - nrows));
+    P[c * a.pitch + r] = N_::zero();
+  }
+  __syncthreads();
+  // ---- T factor.  Z = V^H V over this CTA's rows on the FP64 tensor pipe (4 x 4 tiles of 8 x 8, upper
+  //      tiles only, two per warp), summed over the cluster; T = (striu(Z) + diag(1/tau))^-1. ---------
+  {
+    constexpr bool CPLX = (sizeof(T) == 16);
+    const int gq = lane >> 2, tq = lane & 3;
+    const int gm = warp >> 1, gn0 = (warp & 1) * 2;
+    double g[2][CPLX ? 4 : 2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int r = 0; r < (CPLX ? 4 : 2); ++r) g[j][r] = 0.0;
+    if (gn0 + 1 >= gm) {
+      const T* pa = P + (gm * 8 + gq) * a.pitch + tq;
+      const T* pb0 = P + (gn0 * 8 + gq) * a.pitch + tq;
+      const T* pb1 = pb0 + 8 * a.pitch;
+#pragma unroll 4
+      for (int k0 = 0; k0 < K4; k0 += 4) {
+        const T av = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
+        if constexpr (CPLX) {
+          const double nay = -av.y;
+          dmma884(g[0][0], g[0][1], av.x, b0.x);
+          dmma884(g[0][2], g[0][3], av.x, b0.y);
+          dmma884(g[1][0], g[1][1], av.x, b1.x);
+          dmma884(g[1][2], g[1][3], av.x, b1.y);
+          dmma884(g[0][0], g[0][1], av.y, b0.y);
+          dmma884(g[0][2], g[0][3], nay, b0.x);
+          dmma884(g[1][0], g[1][1], av.y, b1.y);
+          dmma884(g[1][2], g[1][3], nay, b1.x);
+        } else {
+          dmma884(g[0][0], g[0][1], av, b0);
+          dmma884(g[1][0], g[1][1], av, b1);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = gm * 8 + gq, c = (gn0 + j) * 8 + 2 * tq;
+      if constexpr (CPLX) {
+        Z[r * QR_NB + c] = make_double2(g[j][0], g[j][2]);
+        Z[r * QR_NB + c + 1] = make_double2(g[j][1], g[j][3]);
+      } else {
+        Z[r * QR_NB + c] = g[j][0];
+        Z[r * QR_NB + c + 1] = g[j][1];
+      }
     }
   }
   cluster.sync();
@@ -223,49 +266,41 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
     for (int idx = tid; idx < jb * jb; idx += QR_THREADS) {
       const int i = idx / jb, c = idx - i * jb;
       if (i >= c) continue;
-      T s = N_::zero();
-      for (int q = 0; q < C; ++q) s = N_::add(s, cluster.map_shared_rank(Z, q)[i * QR_NB + c]);
-      Z[i * QR_NB + c] = s;  // only CTA 0's copy holds the total; the others are just read
+      T sum = N_::zero();
+      for (int q = 0; q < C; ++q) sum = N_::add(sum, cluster.map_shared_rank(Z, q)[i * QR_NB + c]);
+      Z[i * QR_NB + c] = sum;  // only CTA 0's copy holds the total; the others are just read
     }
   }
   cluster.sync();  // totals complete, and no CTA exits while its Z is still being read
   if (crank == 0 && warp == 0) {
-    // T is upper triangular (LAPACK larft, forward/columnwise):
-    //   T[c][c] = tau_c,  T[0:c, c] = -tau_c * T[0:c, 0:c] * z[0:c, c].
-    // It is built in Z's lower triangle, transposed: T[i][c] lives at Z[c][i], i <= c;
-    // the strictly upper part of Z keeps z.
-    for (int c = 0; c < jb; ++c) {
-      const T tc = tau[c];
-      T mine = N_::zero();
-      if (lane < c) {
-        T s = N_::zero();
-        for (int q = lane; q < c; ++q) s = N_::add(s, N_::mul(Z[q * QR_NB + lane], Z[q * QR_NB + c]));
-        mine = N_::mul(N_::sub(N_::zero(), tc), s);
+    // T is upper triangular with T^-1 = striu(V^H V) + diag(1/tau) (equivalent to LAPACK larft, forward /
+    // columnwise).  Lane c solves for column c by back substitution:
+    //   t_c = tau_c,  t_i = -tau_i * sum_{q = i+1..c} z[i][q] t_q   (tau_i = 0 gives a zero row, as larft).
+    // Column c is kept in the lower triangle of Z, transposed: T[i][c] lives at Z[c][i], i <= c, so the lanes
+    // never touch each other's entries nor the strictly upper part that holds z.
+    const int c = lane;
+    if (c < jb) {
+      Z[c * QR_NB + c] = tau[c];
+      for (int i = c - 1; i >= 0; --i) {
+        T sum = N_::zero();
+        for (int q = i + 1; q <= c; ++q) sum = N_::fma(Z[i * QR_NB + q], Z[c * QR_NB + q], sum);
+        Z[c * QR_NB + i] = N_::mul(N_::sub(N_::zero(), tau[i]), sum);
       }
-      __syncwarp();
-      if (lane < c) Z[c * QR_NB + lane] = mine;
-      if (lane == c) Z[c * QR_NB + c] = tc;
-      __syncwarp();
     }
+    __syncwarp();
     T* Tg = reinterpret_cast<T*>(a.T);
     for (int idx = lane; idx < jb * jb; idx += 32) {
-      const int i = idx / jb, c = idx - i * jb;
+      const int i = idx / jb, cc = idx - i * jb;
       T v = N_::zero();
-      if (i <= c) v = Z[c * QR_NB + i];
-      Tg[i * a.ldt + c] = v;
+      if (i <= cc) v = Z[cc * QR_NB + i];
+      Tg[i * a.ldt + cc] = v;
     }
   }
 
-  // ---- write back: R entries of the first jb rows, explicit V for every row ----------------------
+  // ---- explicit V for every row ------------------------------------------------------------------
   for (int i = tid; i < nrows * jb; i += QR_THREADS) {
     const int r = i / jb, c = i - r * jb;
-    const int64_t pr = r_lo + r;  // panel row
-    const T val = P[c * a.pitch + r];
-    if (pr <= c) Wg[(a.j0 + pr) * a.ldw + a.j0 + c] = val;
-    T v = N_::zero();
-    if (pr > c) v = val;
-    else if (pr == c) v = N_::one();
-    Vg[(a.j0 + pr) * a.ldv + a.j0 + c] = v;
+    Vg[(a.j0 + r_lo + r) * a.ldv + a.j0 + c] = P[c * a.pitch + r];
   }
 }
 
@@ -376,7 +411,7 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
   size_t smem = 0;
   for (;; C *= 2) {
     rows_per = (int)((mr + C - 1) / C);
-    pitch = rows_per | 1;  // odd pitch: the transposing load is conflict-free
+    pitch = ((rows_per + 3) & ~3) + 1;  // odd (conflict-free transposing load), with room for the k4 zero padding
     smem = (size_t)QR_NB * pitch * sizeof(T) + fixed;
     if (smem <= 200 * 1024) break;
     if (C >= 16) return TNB_E_UNSUPPORTED;  // panel taller than 16 CTAs can hold

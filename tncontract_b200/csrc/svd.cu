@@ -58,13 +58,14 @@ int permute_view(int dtype, const void* in, int rank, const int64_t* oshape, con
 
 constexpr int JB = 16;       // Jacobi block width (columns)
 constexpr int JP = 2 * JB;   // columns in a block pair
-constexpr int JT = 256;      // threads per CTA = (JP/2)^2: thread (a, b) owns a 2x2 block
+constexpr int JT = 512;      // threads per CTA: 2 x (JP/2)^2 -- G blocks on the first half, W blocks on the second
 constexpr int JGP = JP + 4;  // pitch of the small matrices in shared memory (= 4 mod 8: conflict-free DMMA fragments)
 constexpr int JPAD = 4;      // panel pitch = CH + JPAD for the same reason
 constexpr int MAX_SWEEPS = 60;
 
 struct JacobiFlags {
-  unsigned long long maxoff_bits;  // max squared off-diagonal cosine of the sweep in flight (double bits)
+  unsigned int state;  // rotation flags of the sweep in flight (see jacobi_finish_sweep_kernel)
+  unsigned int pad0;
   int converged;
   int sweeps;  // completed sweeps (stops counting once converged)
   int bad;     // a non-finite singular value was produced (NaN / Inf input)
@@ -99,31 +100,31 @@ template <> __device__ __forceinline__ double abs_t<cplx>(cplx v) { return hypot
 
 // Rotation J = [[c, sp], [-conj(sp), c]] acting on columns (x_p, x_q) -> (x_p, x_q) J that
 // annihilates x_p^H x_q; identity when the pair is already orthogonal to `tol`.
-template <typename T> struct Rot { double c; T sp; double off; };
+template <typename T> struct Rot { double c; T sp; };
 
-// `off` is the SQUARED cosine |g|^2 / (alpha beta); `tol2` the squared tolerance.  With
-// tau = (beta - alpha)/2 and h = sqrt(tau^2 + |g|^2):  t = sign(tau) |g| / (|tau| + h),
-// c = 1/sqrt(1 + t^2), sp = c t g/|g| = g * sign(tau) c / (|tau| + h)  -- one sqrt, one
-// reciprocal, one rsqrt, no hypot (X is scaled to unit Frobenius norm, nothing overflows).
+// Rotation J = [[c, sp], [-conj(sp), c]] for the pair (p, q) from alpha = G[p][p], beta = G[q][q],
+// g = G[p][q].  With tau = (beta - alpha)/2 and rh = 1/sqrt(tau^2 + |g|^2) (cos 2theta = |tau| rh):
+//   c^2 = (1 + |tau| rh)/2,  sp = g sign(tau) rh / (2 c)       (|theta| <= pi/4, the inner rotation)
+// -- two rsqrt, no division, no square root (X has unit Frobenius norm: nothing overflows).
+// The pair counts as converged when |g|^2 <= tol2 alpha beta; bit 0 of `state` records a rotation,
+// bit 1 one whose squared cosine exceeded 1e-20 (see jacobi_finish_sweep_kernel).
 template <typename T>
-__device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol2) {
+__device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol2, unsigned& state) {
   typedef Num<T> N_;
   Rot<T> r;
-  r.c = 1.0; r.sp = N_::zero(); r.off = 0.0;
+  r.c = 1.0; r.sp = N_::zero();
   const double alpha = N_::real(G[p * JGP + p]), beta = N_::real(G[q * JGP + q]);
   const T gam = G[p * JGP + q];
   const double ag2 = N_::abs2(gam);
   const double ab = alpha * beta;
-  if (ab > 0.0 && ag2 > 0.0) {
-    r.off = ag2 / ab;
-    if (r.off > tol2) {
-      const double tau = 0.5 * (beta - alpha);
-      const double h = sqrt(tau * tau + ag2);
-      const double d = 1.0 / (fabs(tau) + h);
-      const double t2 = ag2 * d * d;
-      r.c = rsqrt(1.0 + t2);
-      r.sp = N_::scale(gam, copysign(r.c * d, tau));
-    }
+  if (ab > 0.0 && ag2 > tol2 * ab) {
+    state |= (ag2 > 1e-20 * ab) ? 3u : 1u;
+    const double tau = 0.5 * (beta - alpha);
+    const double rh = rsqrt(fma(tau, tau, ag2));
+    const double c2 = fma(0.5 * fabs(tau), rh, 0.5);
+    const double rc = rsqrt(c2);
+    r.c = c2 * rc;
+    r.sp = N_::scale(gam, copysign(0.5 * rh * rc, tau));
   }
   return r;
 }
@@ -136,10 +137,17 @@ template <> __device__ __forceinline__ cplx shfl_t<cplx>(cplx v, int src) {
   return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
 
-// Shared memory: P[JP][CH+JPAD] | G[JP][JGP] | Gpart[JP][JGP] | W[JP][JGP]
+// c * x + s * y  (c real, s complex or real), written as FMA chains
+__device__ __forceinline__ double rot_mix(double c, double x, double s, double y) { return fma(c, x, s * y); }
+__device__ __forceinline__ cplx rot_mix(double c, cplx x, cplx s, cplx y) {
+  return make_double2(fma(c, x.x, fma(s.x, y.x, -(s.y * y.y))), fma(c, x.y, fma(s.x, y.y, s.y * y.x)));
+}
+
+// Shared memory: P[JP][CH+JPAD] | G[JP][JGP] | W[JP][JGP]  (the cluster-reduction partials live in W's space)
 template <typename T>
 __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   typedef Num<T> N_;
+  constexpr bool CPLX = (sizeof(T) == 16);
   if (a.flags->converged) return;  // uniform over the whole grid
   cg::cluster_group cluster = cg::this_cluster();
   const int S = a.S;
@@ -153,10 +161,10 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   const int CH = a.CH, pitch = CH + JPAD;
   T* P = reinterpret_cast<T*>(smem_raw);
   T* G = P + (size_t)JP * pitch;
-  T* Gpart = G + JP * JGP;
-  T* W = Gpart + JP * JGP;
+  T* W = G + JP * JGP;
+  T* Gpart = W;
 
-  const int tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   T* Xg = reinterpret_cast<T*>(a.X);
   T* Vg = reinterpret_cast<T*>(a.V);
 
@@ -181,16 +189,12 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   };
 
   // ---- partial Gram matrix of this CTA's Xt chunks on the FP64 tensor pipe (DMMA.8x8x4) ----------
-  // G[p][q] = sum_c conj(P[p][c]) P[q][c]: 4 x 4 tiles of 8 x 8, two per warp; both fragments are rows of P
-  // with c (= k) contiguous, lane (gq, tq) holds element [row0 + gq][k0 + tq].
-  constexpr bool CPLX = (sizeof(T) == 16);
-  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-  double g[2][CPLX ? 4 : 2];
+  // G[p][q] = sum_c conj(P[p][c]) P[q][c]: 4 x 4 tiles of 8 x 8, one per warp; both fragments are rows
+  // of P with c (= k) contiguous, lane (gq, tq) holds element [row0 + gq][k0 + tq].
+  double g[CPLX ? 4 : 2];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int r = 0; r < (CPLX ? 4 : 2); ++r) g[j][r] = 0.0;
-  const int gm = warp >> 1, gn0 = (warp & 1) * 2;
+  for (int r = 0; r < (CPLX ? 4 : 2); ++r) g[r] = 0.0;
+  const int gm = warp >> 2, gn = warp & 3;
   int resident = -1;
   for (int gch = crank; gch < a.nx; gch += S) {
     __syncthreads();
@@ -198,134 +202,123 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     __syncthreads();
     resident = gch;
     const T* pa = P + (gm * 8 + gq) * pitch + tq;
-    const T* pb0 = P + (gn0 * 8 + gq) * pitch + tq;
-    const T* pb1 = pb0 + 8 * pitch;
-#pragma unroll 4
+    const T* pb = P + (gn * 8 + gq) * pitch + tq;
+#pragma unroll 8
     for (int k0 = 0; k0 < CH; k0 += 4) {
-      const T av = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
+      const T av = pa[k0], bv = pb[k0];
       if constexpr (CPLX) {
-        const double nay = -av.y;
-        dmma884(g[0][0], g[0][1], av.x, b0.x);
-        dmma884(g[0][2], g[0][3], av.x, b0.y);
-        dmma884(g[1][0], g[1][1], av.x, b1.x);
-        dmma884(g[1][2], g[1][3], av.x, b1.y);
-        dmma884(g[0][0], g[0][1], av.y, b0.y);
-        dmma884(g[0][2], g[0][3], nay, b0.x);
-        dmma884(g[1][0], g[1][1], av.y, b1.y);
-        dmma884(g[1][2], g[1][3], nay, b1.x);
+        dmma884(g[0], g[1], av.x, bv.x);
+        dmma884(g[2], g[3], av.x, bv.y);
+        dmma884(g[0], g[1], av.y, bv.y);
+        dmma884(g[2], g[3], -av.y, bv.x);
       } else {
-        dmma884(g[0][0], g[0][1], av, b0);
-        dmma884(g[1][0], g[1][1], av, b1);
+        dmma884(g[0], g[1], av, bv);
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int r = gm * 8 + gq, c = (gn0 + j) * 8 + 2 * tq;
+  {
+    const int r = gm * 8 + gq, c = gn * 8 + 2 * tq;
     if constexpr (CPLX) {
-      Gpart[r * JGP + c] = make_double2(g[j][0], g[j][2]);
-      Gpart[r * JGP + c + 1] = make_double2(g[j][1], g[j][3]);
+      Gpart[r * JGP + c] = make_double2(g[0], g[2]);
+      Gpart[r * JGP + c + 1] = make_double2(g[1], g[3]);
     } else {
-      Gpart[r * JGP + c] = g[j][0];
-      Gpart[r * JGP + c + 1] = g[j][1];
+      Gpart[r * JGP + c] = g[0];
+      Gpart[r * JGP + c + 1] = g[1];
     }
-  }
-  for (int idx = tid; idx < JP * JP; idx += JT) {
-    const int i = idx / JP, j = idx - i * JP;
-    W[i * JGP + j] = (i == j) ? N_::one() : N_::zero();
   }
   cluster.sync();
   for (int idx = tid; idx < JP * JP; idx += JT) {
     const int i = idx / JP, j = idx - i * JP;
-    T s = N_::zero();
-    for (int q = 0; q < S; ++q) s = N_::add(s, cluster.map_shared_rank(Gpart, q)[i * JGP + j]);
-    G[i * JGP + j] = s;
+    T sum = N_::zero();
+    for (int q = 0; q < S; ++q) sum = N_::add(sum, cluster.map_shared_rank(Gpart, q)[i * JGP + j]);
+    G[i * JGP + j] = sum;
   }
-  cluster.sync();  // all remote reads done before any CTA moves on (or exits)
+  cluster.sync();  // all remote reads done before any CTA overwrites its partials (or exits)
+  for (int idx = tid; idx < JP * JP; idx += JT) {
+    const int i = idx / JP, j = idx - i * JP;
+    W[i * JGP + j] = (i == j) ? N_::one() : N_::zero();
+  }
+  __syncthreads();
 
-  // ---- one parallel-ordered Jacobi sweep on G, rotations accumulated in W ------------
-  double maxoff = 0.0;  // squared cosine
+  // ---- one parallel-ordered Jacobi sweep on G, rotations accumulated in W ------------------------
+  // 31 steps of 16 disjoint rotations.  Threads 0..255: thread (ta, tb) owns the 2 x 2 block of G
+  // between rotation pairs ta and tb (B' = J_a^H B J_b).  Threads 256..511: rows 2ta, 2ta+1 of W times
+  // J_b.  Every thread builds the rotation of pair tb = lane & 15; the one of pair ta comes from lane ta.
+  const int role = tid >> 8, ta = (tid & 255) >> 4, tb = tid & 15;
   const double tol2 = a.tol * a.tol;
+  unsigned state = 0;
   for (int step = 0; step < JP - 1; ++step) {
     int pa, qa, pb, qb;
     rr_pair(JP, step, ta, pa, qa);
     rr_pair(JP, step, tb, pb, qb);
     if (pa > qa) { const int t = pa; pa = qa; qa = t; }
     if (pb > qb) { const int t = pb; pb = qb; qb = t; }
-    // every thread builds the rotation of pair tb = lane & 15; the one of pair ta comes from lane ta
-    const Rot<T> Rb = make_rot<T>(G, pb, qb, tol2);
+    const Rot<T> Rb = make_rot<T>(G, pb, qb, tol2, state);
     Rot<T> Ra;
     Ra.c = __shfl_sync(0xffffffffu, Rb.c, ta);
     Ra.sp = shfl_t<T>(Rb.sp, ta);
-    Ra.off = Rb.off;  // only used when ta == tb
-    const T b00 = G[pa * JGP + pb], b01 = G[pa * JGP + qb], b10 = G[qa * JGP + pb], b11 = G[qa * JGP + qb];
-    const T w00 = W[(2 * ta) * JGP + pb], w01 = W[(2 * ta) * JGP + qb];
-    const T w10 = W[(2 * ta + 1) * JGP + pb], w11 = W[(2 * ta + 1) * JGP + qb];
-    __syncthreads();
-    // T1 = B J_b
-    const T csb = N_::conj(Rb.sp);
-    const T t00 = N_::sub(N_::scale(b00, Rb.c), N_::mul(csb, b01));
-    const T t01 = N_::add(N_::mul(Rb.sp, b00), N_::scale(b01, Rb.c));
-    const T t10 = N_::sub(N_::scale(b10, Rb.c), N_::mul(csb, b11));
-    const T t11 = N_::add(N_::mul(Rb.sp, b10), N_::scale(b11, Rb.c));
-    // B' = J_a^H T1,  J_a^H = [[c, -sp], [conj(sp), c]]
-    const T csa = N_::conj(Ra.sp);
-    T n00 = N_::sub(N_::scale(t00, Ra.c), N_::mul(Ra.sp, t10));
-    T n01 = N_::sub(N_::scale(t01, Ra.c), N_::mul(Ra.sp, t11));
-    T n10 = N_::add(N_::mul(csa, t00), N_::scale(t10, Ra.c));
-    T n11 = N_::add(N_::mul(csa, t01), N_::scale(t11, Ra.c));
-    if (ta == tb) {
-      // diagonal block: real diagonal, exact zero where a rotation was applied
-      n00 = N_::from(N_::real(n00), 0.0);
-      n11 = N_::from(N_::real(n11), 0.0);
-      if (Ra.c != 1.0 || N_::abs2(Ra.sp) != 0.0) { n01 = N_::zero(); n10 = N_::zero(); }
-      if (Ra.off > maxoff) maxoff = Ra.off;
+    const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));  // -conj(sp_b)
+    if (role == 0) {
+      const T b00 = G[pa * JGP + pb], b01 = G[pa * JGP + qb], b10 = G[qa * JGP + pb], b11 = G[qa * JGP + qb];
+      __syncthreads();
+      // T1 = B J_b:  T1[:,0] = c B[:,0] - conj(sp) B[:,1],  T1[:,1] = sp B[:,0] + c B[:,1]
+      const T t00 = rot_mix(Rb.c, b00, msb, b01), t01 = rot_mix(Rb.c, b01, Rb.sp, b00);
+      const T t10 = rot_mix(Rb.c, b10, msb, b11), t11 = rot_mix(Rb.c, b11, Rb.sp, b10);
+      // B' = J_a^H T1,  J_a^H = [[c, -sp], [conj(sp), c]]
+      const T msa = N_::sub(N_::zero(), Ra.sp), csa = N_::conj(Ra.sp);
+      T n00 = rot_mix(Ra.c, t00, msa, t10), n01 = rot_mix(Ra.c, t01, msa, t11);
+      T n10 = rot_mix(Ra.c, t10, csa, t00), n11 = rot_mix(Ra.c, t11, csa, t01);
+      if (ta == tb) {
+        // diagonal block: real diagonal, exact zero where a rotation was applied
+        n00 = N_::from(N_::real(n00), 0.0);
+        n11 = N_::from(N_::real(n11), 0.0);
+        if (Ra.c != 1.0 || N_::abs2(Ra.sp) != 0.0) { n01 = N_::zero(); n10 = N_::zero(); }
+      }
+      G[pa * JGP + pb] = n00; G[pa * JGP + qb] = n01; G[qa * JGP + pb] = n10; G[qa * JGP + qb] = n11;
+    } else {
+      const T w00 = W[(2 * ta) * JGP + pb], w01 = W[(2 * ta) * JGP + qb];
+      const T w10 = W[(2 * ta + 1) * JGP + pb], w11 = W[(2 * ta + 1) * JGP + qb];
+      __syncthreads();
+      // W' = W J_b on rows 2ta, 2ta+1
+      W[(2 * ta) * JGP + pb] = rot_mix(Rb.c, w00, msb, w01);
+      W[(2 * ta) * JGP + qb] = rot_mix(Rb.c, w01, Rb.sp, w00);
+      W[(2 * ta + 1) * JGP + pb] = rot_mix(Rb.c, w10, msb, w11);
+      W[(2 * ta + 1) * JGP + qb] = rot_mix(Rb.c, w11, Rb.sp, w10);
     }
-    G[pa * JGP + pb] = n00; G[pa * JGP + qb] = n01; G[qa * JGP + pb] = n10; G[qa * JGP + qb] = n11;
-    // W' = W J_b on rows 2ta, 2ta+1
-    W[(2 * ta) * JGP + pb] = N_::sub(N_::scale(w00, Rb.c), N_::mul(csb, w01));
-    W[(2 * ta) * JGP + qb] = N_::add(N_::mul(Rb.sp, w00), N_::scale(w01, Rb.c));
-    W[(2 * ta + 1) * JGP + pb] = N_::sub(N_::scale(w10, Rb.c), N_::mul(csb, w11));
-    W[(2 * ta + 1) * JGP + qb] = N_::add(N_::mul(Rb.sp, w10), N_::scale(w11, Rb.c));
     __syncthreads();
   }
   if (crank == 0) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double other = __shfl_xor_sync(0xffffffffu, maxoff, o);
-      if (other > maxoff) maxoff = other;
-    }
-    if ((tid & 31) == 0 && maxoff > 0.0)
-      atomicMax(&a.flags->maxoff_bits, (unsigned long long)__double_as_longlong(maxoff));
+    state = __reduce_or_sync(0xffffffffu, state);
+    if (lane == 0 && state) atomicOr(&a.flags->state, state);
   }
 
   // ---- rows_new[q] = sum_p W[p][q] rows[p] on every chunk of this CTA, again on DMMA: per warp a
-  //      32 (q) x 32 (c) x 32 (p) product; A[m = q][k = p] = W[p][q], B[k = p][n = c] = P[p][c].
-  //      A warp reads and rewrites only its own 32 columns of P, so the result goes back into P in
-  //      place and is stored to global memory with full 512-byte row segments.
+  //      32 (q) x 16 (c) x 32 (p) product; A[m = q][k = p] = W[p][q], B[k = p][n = c] = P[p][c].
+  //      A warp reads and rewrites only its own 16 columns of P, so the result goes back into P in
+  //      place and is stored to global memory as full row segments.
   auto apply_chunk = [&](int gch) {
     T* base; int64_t ld, c0; int len;
     chunk_geom(gch, base, ld, c0, len);
-    for (int cw = warp * 32; cw < CH; cw += 8 * 32) {
+    for (int cw = warp * 16; cw < CH; cw += (JT / 32) * 16) {
       if (cw >= len) break;
-      double acc[4][4][CPLX ? 4 : 2];
+      double acc[4][2][CPLX ? 4 : 2];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
           for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[mt][nt][r] = 0.0;
 #pragma unroll 2
       for (int k0 = 0; k0 < JP; k0 += 4) {
-        T av[4], bv[4];
+        T av[4], bv[2];
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JGP + mt * 8 + gq];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) bv[nt] = P[(k0 + tq) * pitch + cw + nt * 8 + gq];
+        for (int nt = 0; nt < 2; ++nt) bv[nt] = P[(k0 + tq) * pitch + cw + nt * 8 + gq];
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
+          for (int nt = 0; nt < 2; ++nt) {
             if constexpr (CPLX) {
               dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt].x, bv[nt].x);
               dmma884(acc[mt][nt][2], acc[mt][nt][3], av[mt].x, bv[nt].y);
@@ -341,7 +334,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < 2; ++nt) {
           T* dst = P + (mt * 8 + gq) * pitch + cw + nt * 8 + 2 * tq;
           if constexpr (CPLX) {
             dst[0] = make_double2(acc[mt][nt][0], acc[mt][nt][2]);
@@ -352,11 +345,13 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
           }
         }
       __syncwarp();
-      if (cw + lane < len) {
+      // 32 rows x 16 columns: lanes 0-15 take even rows, lanes 16-31 odd rows
+      const int col = cw + (lane & 15);
+      if (col < len) {
 #pragma unroll 4
-        for (int q = 0; q < JP; ++q) {
+        for (int q = (lane >> 4); q < JP; q += 2) {
           const int64_t r = grow(q);
-          if (r >= 0) base[r * ld + c0 + cw + lane] = P[q * pitch + cw + lane];
+          if (r >= 0) base[r * ld + c0 + col] = P[q * pitch + col];
         }
       }
     }
@@ -371,14 +366,14 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   }
 }
 
-__global__ void jacobi_finish_sweep_kernel(JacobiFlags* f, double tol) {
+// Closes a sweep.  state bit 0: some pair was rotated (cosine above tol); bit 1: some rotated pair had a
+// squared cosine above 1e-20.  Cyclic Jacobi converges quadratically, so a sweep whose largest cosine was
+// already below 1e-10 leaves every cosine far below tol: the confirming sweep is skipped.
+__global__ void jacobi_finish_sweep_kernel(JacobiFlags* f) {
   if (f->converged) return;
-  const double off2 = __longlong_as_double((long long)f->maxoff_bits);  // squared cosine
   f->sweeps += 1;
-  // Cyclic Jacobi converges quadratically: a sweep that STARTED with every cosine below 1e-10 leaves
-  // them far below tol, so the confirming sweep is skipped (it would only re-measure).
-  if (off2 <= tol * tol || off2 <= 1e-20) f->converged = 1;
-  f->maxoff_bits = 0ull;
+  if ((f->state & 2u) == 0u) f->converged = 1;
+  f->state = 0u;
 }
 
 // sigma[j] = |Xt[j, :]|, one warp per row (scaled two-pass-free: values are O(|A|), no overflow risk
@@ -537,11 +532,11 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
   int S = 1;
   while (S * 2 <= 8 && S * 2 <= a.nx + a.nv && npairs * S * 2 <= sm_count()) S *= 2;
   a.S = S;
-  const size_t smem = ((size_t)JP * (CH + JPAD) + 3 * (size_t)JP * JGP) * sizeof(T);
+  const size_t smem = ((size_t)JP * (CH + JPAD) + 2 * (size_t)JP * JGP) * sizeof(T);
   TNB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(JacobiFlags), st));
   int queued = 0;
   JacobiFlags h;
-  h.converged = 0; h.sweeps = 0; h.maxoff_bits = 0;
+  h.converged = 0; h.sweeps = 0; h.state = 0;
   while (queued < MAX_SWEEPS) {
     const int batch = (queued == 0) ? 5 : 2;
     for (int s = 0; s < batch; ++s) {
@@ -553,7 +548,7 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
         int rc = launch_round<T>(a, npairs, smem, st);
         if (rc) return rc;
       }
-      jacobi_finish_sweep_kernel<<<1, 1, 0, st>>>(flags, a.tol);
+      jacobi_finish_sweep_kernel<<<1, 1, 0, st>>>(flags);
       TNB_LAUNCH_CHECK();
     }
     queued += batch;
