@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
         const int c = j + warp + QR_WARPS * i;
         xc[i] = P + (c < jb ? c : j) * a.pitch;
       }
+#pragma unroll 4
       for (int r = lo + lane; r < nrows; r += 32) {
         const T x = xj[r];
 #pragma unroll
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
         const T f = N_::mul(N_::conj(tau_j), w);
         const T fs = N_::mul(f, scale);
         T* xcc = P + c * a.pitch;
+#pragma unroll 4
         for (int r = lo1 + lane; r < nrows; r += 32) xcc[r] = N_::sub(xcc[r], N_::mul(fs, xj[r]));
         if (own_diag && lane == 0) xcc[jl] = N_::sub(xcc[jl], f);  // v_j = 1 on the diagonal
       }
