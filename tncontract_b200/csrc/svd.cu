@@ -143,7 +143,7 @@ __device__ __forceinline__ cplx rot_mix(double c, cplx x, cplx s, cplx y) {
   return make_double2(fma(c, x.x, fma(s.x, y.x, -(s.y * y.y))), fma(c, x.y, fma(s.x, y.y, s.y * y.x)));
 }
 
-// Shared memory: P[JP][CH+JPAD] | G[JP][JGP] | W[JP][JGP]  (the cluster-reduction partials live in W's space)
+// Shared memory: P[JP][CH+JPAD] | G[2][JP][JGP] | W[2][JP][JGP]  (the cluster-reduction partials live in W's space)
 template <typename T>
 __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   typedef Num<T> N_;
@@ -160,11 +160,19 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = a.CH, pitch = CH + JPAD;
   T* P = reinterpret_cast<T*>(smem_raw);
-  T* G = P + (size_t)JP * pitch;
-  T* W = G + JP * JGP;
+  T* G = P + (size_t)JP * pitch;   // G and W are double-buffered through the sweep: [2][JP][JGP] each
+  T* W = G + 2 * JP * JGP;
   T* Gpart = W;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  // s_rr[step][a] = (smaller, larger) column of rotation pair a in step `step` of the 32-column tournament
+  __shared__ unsigned char s_rr[JP - 1][JP / 2][2];
+  if (tid < (JP - 1) * (JP / 2)) {
+    int x, y;
+    rr_pair(JP, tid / (JP / 2), tid % (JP / 2), x, y);
+    s_rr[tid / (JP / 2)][tid % (JP / 2)][0] = (unsigned char)(x < y ? x : y);
+    s_rr[tid / (JP / 2)][tid % (JP / 2)][1] = (unsigned char)(x < y ? y : x);
+  }
   T* Xg = reinterpret_cast<T*>(a.X);
   T* Vg = reinterpret_cast<T*>(a.V);
 
@@ -244,23 +252,24 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   // 31 steps of 16 disjoint rotations.  Threads 0..255: thread (ta, tb) owns the 2 x 2 block of G
   // between rotation pairs ta and tb (B' = J_a^H B J_b).  Threads 256..511: rows 2ta, 2ta+1 of W times
   // J_b.  Every thread builds the rotation of pair tb = lane & 15; the one of pair ta comes from lane ta.
+  // G and W ping-pong between two buffers, so a step needs a single barrier.
   const int role = tid >> 8, ta = (tid & 255) >> 4, tb = tid & 15;
   const double tol2 = a.tol * a.tol;
   unsigned state = 0;
   for (int step = 0; step < JP - 1; ++step) {
-    int pa, qa, pb, qb;
-    rr_pair(JP, step, ta, pa, qa);
-    rr_pair(JP, step, tb, pb, qb);
-    if (pa > qa) { const int t = pa; pa = qa; qa = t; }
-    if (pb > qb) { const int t = pb; pb = qb; qb = t; }
-    const Rot<T> Rb = make_rot<T>(G, pb, qb, tol2, state);
-    Rot<T> Ra;
-    Ra.c = __shfl_sync(0xffffffffu, Rb.c, ta);
-    Ra.sp = shfl_t<T>(Rb.sp, ta);
+    const T* Gc = G + (step & 1) * (JP * JGP);
+    T* Gn = G + ((step & 1) ^ 1) * (JP * JGP);
+    const T* Wc = W + (step & 1) * (JP * JGP);
+    T* Wn = W + ((step & 1) ^ 1) * (JP * JGP);
+    const int pa = s_rr[step][ta][0], qa = s_rr[step][ta][1];
+    const int pb = s_rr[step][tb][0], qb = s_rr[step][tb][1];
+    const Rot<T> Rb = make_rot<T>(Gc, pb, qb, tol2, state);
     const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));  // -conj(sp_b)
     if (role == 0) {
-      const T b00 = G[pa * JGP + pb], b01 = G[pa * JGP + qb], b10 = G[qa * JGP + pb], b11 = G[qa * JGP + qb];
-      __syncthreads();
+      const T b00 = Gc[pa * JGP + pb], b01 = Gc[pa * JGP + qb], b10 = Gc[qa * JGP + pb], b11 = Gc[qa * JGP + qb];
+      Rot<T> Ra;
+      Ra.c = __shfl_sync(0xffffffffu, Rb.c, ta);
+      Ra.sp = shfl_t<T>(Rb.sp, ta);
       // T1 = B J_b:  T1[:,0] = c B[:,0] - conj(sp) B[:,1],  T1[:,1] = sp B[:,0] + c B[:,1]
       const T t00 = rot_mix(Rb.c, b00, msb, b01), t01 = rot_mix(Rb.c, b01, Rb.sp, b00);
       const T t10 = rot_mix(Rb.c, b10, msb, b11), t11 = rot_mix(Rb.c, b11, Rb.sp, b10);
@@ -274,19 +283,19 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         n11 = N_::from(N_::real(n11), 0.0);
         if (Ra.c != 1.0 || N_::abs2(Ra.sp) != 0.0) { n01 = N_::zero(); n10 = N_::zero(); }
       }
-      G[pa * JGP + pb] = n00; G[pa * JGP + qb] = n01; G[qa * JGP + pb] = n10; G[qa * JGP + qb] = n11;
+      Gn[pa * JGP + pb] = n00; Gn[pa * JGP + qb] = n01; Gn[qa * JGP + pb] = n10; Gn[qa * JGP + qb] = n11;
     } else {
-      const T w00 = W[(2 * ta) * JGP + pb], w01 = W[(2 * ta) * JGP + qb];
-      const T w10 = W[(2 * ta + 1) * JGP + pb], w11 = W[(2 * ta + 1) * JGP + qb];
-      __syncthreads();
+      const T w00 = Wc[(2 * ta) * JGP + pb], w01 = Wc[(2 * ta) * JGP + qb];
+      const T w10 = Wc[(2 * ta + 1) * JGP + pb], w11 = Wc[(2 * ta + 1) * JGP + qb];
       // W' = W J_b on rows 2ta, 2ta+1
-      W[(2 * ta) * JGP + pb] = rot_mix(Rb.c, w00, msb, w01);
-      W[(2 * ta) * JGP + qb] = rot_mix(Rb.c, w01, Rb.sp, w00);
-      W[(2 * ta + 1) * JGP + pb] = rot_mix(Rb.c, w10, msb, w11);
-      W[(2 * ta + 1) * JGP + qb] = rot_mix(Rb.c, w11, Rb.sp, w10);
+      Wn[(2 * ta) * JGP + pb] = rot_mix(Rb.c, w00, msb, w01);
+      Wn[(2 * ta) * JGP + qb] = rot_mix(Rb.c, w01, Rb.sp, w00);
+      Wn[(2 * ta + 1) * JGP + pb] = rot_mix(Rb.c, w10, msb, w11);
+      Wn[(2 * ta + 1) * JGP + qb] = rot_mix(Rb.c, w11, Rb.sp, w10);
     }
     __syncthreads();
   }
+  W += ((JP - 1) & 1) * (JP * JGP);  // the buffer the last step wrote
   if (crank == 0) {
     state = __reduce_or_sync(0xffffffffu, state);
     if (lane == 0 && state) atomicOr(&a.flags->state, state);
@@ -532,7 +541,8 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
   int S = 1;
   while (S * 2 <= 8 && S * 2 <= a.nx + a.nv && npairs * S * 2 <= sm_count()) S *= 2;
   a.S = S;
-  const size_t smem = ((size_t)JP * (CH + JPAD) + 2 * (size_t)JP * JGP) * sizeof(T);
+  const size_t smem = ((size_t)JP * (CH + JPAD) + 4 * (size_t)JP * JGP) * sizeof(T);
+
   TNB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(JacobiFlags), st));
   int queued = 0;
   JacobiFlags h;
