@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtnb.so")
+LIB_PATH = os.environ.get("TNB_LIB_PATH") or os.path.join(_HERE, "lib", "libtnb.so")  # override: kernel experiments
 
 MAX_RANK = 12
 F64, C128 = 0, 1

@@ -40,6 +40,7 @@
 // xGESVJ).  HBM/L2 traffic per round: Xt and Vt read once and written once.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -80,6 +81,7 @@ struct JacobiArgs {
   int64_t ldx, ldv;
   int nblk;     // even number of column blocks (the last ones may be empty)
   int round;
+  int diag;     // 1: rotate the pairs INSIDE each of the two blocks (15 steps); 0: the 16 x 16 cross pairs (16 steps)
   int S;        // CTAs per cluster
   int CH;       // chunk length (power of two)
   int nx, nv;   // chunks per Xt row / per Vt row
@@ -165,13 +167,24 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   T* Gpart = W;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-  // s_rr[step][a] = (smaller, larger) column of rotation pair a in step `step` of the 32-column tournament
-  __shared__ unsigned char s_rr[JP - 1][JP / 2][2];
-  if (tid < (JP - 1) * (JP / 2)) {
+  // s_rr[step][a] = (smaller, larger) panel column of rotation pair a in step `step`.
+  //   cross round: column a of block I meets column (a + step) mod 16 of block J      (16 steps)
+  //   diag  round: two independent 16-player tournaments, one inside each block       (15 steps)
+  // One diag round plus nblk - 1 cross rounds rotate every column pair exactly once per sweep.
+  __shared__ unsigned char s_rr[JB][JP / 2][2];
+  const int nsteps = a.diag ? JB - 1 : JB;
+  if (tid < nsteps * (JP / 2)) {
+    const int st_ = tid / (JP / 2), pr_ = tid % (JP / 2);
     int x, y;
-    rr_pair(JP, tid / (JP / 2), tid % (JP / 2), x, y);
-    s_rr[tid / (JP / 2)][tid % (JP / 2)][0] = (unsigned char)(x < y ? x : y);
-    s_rr[tid / (JP / 2)][tid % (JP / 2)][1] = (unsigned char)(x < y ? y : x);
+    if (a.diag) {
+      rr_pair(JB, st_, pr_ & (JB / 2 - 1), x, y);
+      if (pr_ >= JB / 2) { x += JB; y += JB; }
+    } else {
+      x = pr_;
+      y = JB + ((pr_ + st_) & (JB - 1));
+    }
+    s_rr[st_][pr_][0] = (unsigned char)(x < y ? x : y);
+    s_rr[st_][pr_][1] = (unsigned char)(x < y ? y : x);
   }
   T* Xg = reinterpret_cast<T*>(a.X);
   T* Vg = reinterpret_cast<T*>(a.V);
@@ -211,8 +224,12 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     resident = gch;
     const T* pa = P + (gm * 8 + gq) * pitch + tq;
     const T* pb = P + (gn * 8 + gq) * pitch + tq;
+#ifdef TNB_EXP_SKIP_GRAM
+    for (int k0 = 0; k0 < 4; k0 += 4) {
+#else
 #pragma unroll 8
     for (int k0 = 0; k0 < CH; k0 += 4) {
+#endif
       const T av = pa[k0], bv = pb[k0];
       if constexpr (CPLX) {
         dmma884(g[0], g[1], av.x, bv.x);
@@ -248,15 +265,19 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   }
   __syncthreads();
 
-  // ---- one parallel-ordered Jacobi sweep on G, rotations accumulated in W ------------------------
-  // 31 steps of 16 disjoint rotations.  Threads 0..255: thread (ta, tb) owns the 2 x 2 block of G
+  // ---- parallel-ordered Jacobi rotations on G, accumulated in W --------------------------------------
+  // 16 (cross round) or 15 (diag round) steps of 16 disjoint rotations.  Threads 0..255: thread (ta, tb) owns the 2 x 2 block of G
   // between rotation pairs ta and tb (B' = J_a^H B J_b).  Threads 256..511: rows 2ta, 2ta+1 of W times
   // J_b.  Every thread builds the rotation of pair tb = lane & 15; the one of pair ta comes from lane ta.
   // G and W ping-pong between two buffers, so a step needs a single barrier.
   const int role = tid >> 8, ta = (tid & 255) >> 4, tb = tid & 15;
   const double tol2 = a.tol * a.tol;
   unsigned state = 0;
-  for (int step = 0; step < JP - 1; ++step) {
+#ifdef TNB_EXP_SKIP_EIGEN
+  for (int step = 0; step < 0; ++step) {
+#else
+  for (int step = 0; step < nsteps; ++step) {
+#endif
     const T* Gc = G + (step & 1) * (JP * JGP);
     T* Gn = G + ((step & 1) ^ 1) * (JP * JGP);
     const T* Wc = W + (step & 1) * (JP * JGP);
@@ -295,7 +316,9 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     }
     __syncthreads();
   }
-  W += ((JP - 1) & 1) * (JP * JGP);  // the buffer the last step wrote
+#ifndef TNB_EXP_SKIP_EIGEN
+  W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
+#endif
   if (crank == 0) {
     state = __reduce_or_sync(0xffffffffu, state);
     if (lane == 0 && state) atomicOr(&a.flags->state, state);
@@ -317,8 +340,12 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
           for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[mt][nt][r] = 0.0;
+#ifdef TNB_EXP_SKIP_APPLY
+      for (int k0 = 0; k0 < 4; k0 += 4) {
+#else
 #pragma unroll 2
       for (int k0 = 0; k0 < JP; k0 += 4) {
+#endif
         T av[4], bv[2];
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JGP + mt * 8 + gq];
@@ -378,10 +405,11 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
 // Closes a sweep.  state bit 0: some pair was rotated (cosine above tol); bit 1: some rotated pair had a
 // squared cosine above 1e-20.  Cyclic Jacobi converges quadratically, so a sweep whose largest cosine was
 // already below 1e-10 leaves every cosine far below tol: the confirming sweep is skipped.
-__global__ void jacobi_finish_sweep_kernel(JacobiFlags* f) {
+__global__ void jacobi_finish_sweep_kernel(JacobiFlags* f, int fixed) {
   if (f->converged) return;
   f->sweeps += 1;
-  if ((f->state & 2u) == 0u) f->converged = 1;
+  if (fixed > 0) { if (f->sweeps >= fixed) f->converged = 1; }  // kernel experiments only (TNB_JACOBI_FIXED_SWEEPS)
+  else if ((f->state & 2u) == 0u) f->converged = 1;
   f->state = 0u;
 }
 
@@ -544,6 +572,7 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
   const size_t smem = ((size_t)JP * (CH + JPAD) + 4 * (size_t)JP * JGP) * sizeof(T);
 
   TNB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(JacobiFlags), st));
+  static const int fixed_sweeps = getenv("TNB_JACOBI_FIXED_SWEEPS") ? atoi(getenv("TNB_JACOBI_FIXED_SWEEPS")) : 0;
   int queued = 0;
   JacobiFlags h;
   h.converged = 0; h.sweeps = 0; h.state = 0;
@@ -552,13 +581,14 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
     for (int s = 0; s < batch; ++s) {
       // executed flops of one sweep: per pair and round, a JP x JP Gram over L and W applied over L + n
       ProfScope prof(KC_JACOBI, st, (cplx ? 8.0 : 2.0) * (double)JP * JP * (2.0 * (double)L + (double)n) *
-                                        (double)npairs * (double)rounds);
-      for (int r = 0; r < rounds; ++r) {
-        a.round = r;
+                                        (double)npairs * (double)(rounds + 1));
+      for (int r = -1; r < rounds; ++r) {
+        a.diag = (r < 0);           // first the pairs inside the blocks (paired up as in round 0) ...
+        a.round = (r < 0) ? 0 : r;  // ... then every block against every other block
         int rc = launch_round<T>(a, npairs, smem, st);
         if (rc) return rc;
       }
-      jacobi_finish_sweep_kernel<<<1, 1, 0, st>>>(flags);
+      jacobi_finish_sweep_kernel<<<1, 1, 0, st>>>(flags, fixed_sweeps);
       TNB_LAUNCH_CHECK();
     }
     queued += batch;
