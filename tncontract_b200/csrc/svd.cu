@@ -197,9 +197,34 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     if (g < a.nx) { base = Xg; ld = a.ldx; c0 = (int64_t)g * CH; const int64_t rem = a.L - c0; len = (int)(rem < CH ? rem : CH); }
     else { base = Vg; ld = a.ldv; c0 = (int64_t)(g - a.nx) * CH; const int64_t rem = a.n - c0; len = (int)(rem < CH ? rem : CH); }
   };
+  // Full chunks whose rows are 16-byte aligned move by TMA bulk copies (one 1-D copy per panel row,
+  // issued by the lanes of warp 0, completion on an mbarrier); anything else by plain loads.
+  __shared__ __align__(8) uint64_t s_bar;
+  uint32_t bar_phase = 0;
+  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  auto bulk_ok = [&](const T* base, int64_t ld, int len) -> bool {
+    return len == CH && (CPLX || ((ld & 1) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0));
+  };
   auto load_chunk = [&](int g) {
     T* base; int64_t ld, c0; int len;
     chunk_geom(g, base, ld, c0, len);
+    if (bulk_ok(base, ld, len)) {
+      if (warp == 0) {
+        const int64_t r = grow(lane);
+        const unsigned valid = __ballot_sync(0xffffffffu, r >= 0);
+        if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(__popc(valid) * CH * sizeof(T)));
+        __syncwarp();
+        if (r >= 0) bulk_g2s(P + lane * pitch, base + r * ld + c0, (uint32_t)(CH * sizeof(T)), &s_bar);
+      } else {
+        for (int i = 0; i < JP; ++i) {  // rows past the end of the matrix are zero columns
+          if (grow(i) >= 0) continue;
+          for (int c = tid - 32; c < CH; c += JT - 32) P[i * pitch + c] = N_::zero();
+        }
+      }
+      mbar_wait(&s_bar, bar_phase);
+      bar_phase ^= 1;
+      return;
+    }
     for (int idx = tid; idx < JP * CH; idx += JT) {
       const int i = idx / CH, c = idx - i * CH;
       const int64_t r = grow(i);
@@ -381,14 +406,27 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
           }
         }
       __syncwarp();
-      // 32 rows x 16 columns: lanes 0-15 take even rows, lanes 16-31 odd rows
-      const int col = cw + (lane & 15);
-      if (col < len) {
+      if (!bulk_ok(base, ld, len)) {
+        // 32 rows x 16 columns: lanes 0-15 take even rows, lanes 16-31 odd rows
+        const int col = cw + (lane & 15);
+        if (col < len) {
 #pragma unroll 4
-        for (int q = (lane >> 4); q < JP; q += 2) {
-          const int64_t r = grow(q);
-          if (r >= 0) base[r * ld + c0 + col] = P[q * pitch + col];
+          for (int q = (lane >> 4); q < JP; q += 2) {
+            const int64_t r = grow(q);
+            if (r >= 0) base[r * ld + c0 + col] = P[q * pitch + col];
+          }
         }
+      }
+    }
+    if (bulk_ok(base, ld, len)) {
+      // whole rows go out as TMA bulk stores once every warp has written its columns back into P
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0) {
+        const int64_t r = grow(lane);
+        if (r >= 0) bulk_s2g(base + r * ld + c0, P + lane * pitch, (uint32_t)(CH * sizeof(T)));
+        bulk_commit();
+        bulk_wait_all();  // P may be overwritten (next chunk) or the CTA may exit after this
       }
     }
   };
@@ -633,7 +671,8 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     const int64_t sh[2] = {n, m}, is[2] = {1, lda};
     rc = permute_view(dtype, A, 2, sh, is, AH, 1.0, 0.0, 1, st);
     if (rc) return rc;
-    rc = qr(dtype, n, m, AH, m, Q, R, qr_ws, 2, &qscale, st);
+    // projection mode never uses Q for a wide matrix (U comes from R^H, P = U^H A from A itself)
+    rc = qr(dtype, n, m, AH, m, proj ? (void*)nullptr : (void*)Q, R, qr_ws, 2, &qscale, st);
     if (rc) return rc;
   }
   // Jacobi orthogonalises the columns of X, stored as rows of Xt:
