@@ -36,3 +36,20 @@ if what in ("gemm", "all"):
     timeit("rank-128 update 3072x1408", lambda: dv.tensordot(X, Y, [1], [0]), 8 * 3072 * 1408 * 128)
     a, b = torch.randn(1536, 1536, dtype=torch.complex128, device="cuda"), torch.randn(1536, 3072, dtype=torch.complex128, device="cuda")
     timeit("cuBLAS zgemm 1536x1536x3072", lambda: torch.matmul(a, b), 8 * 1536 * 1536 * 3072)
+if what in ("qrprof",):
+    import ctypes
+    lib = _lib.load()
+    names = ["gemm", "jacobi_round", "qr_panel", "permute", "mps_mpo_site", "elementwise"]
+    for shape in ((3072, 1536), (1536, 1024)):
+        B = rn(*shape)
+        dv.qr(B); torch.cuda.synchronize()
+        lib.tnb_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); dv.qr(B); e1.record(); e1.synchronize()
+        print("qr", shape, "total %.3f ms" % e0.elapsed_time(e1))
+        for c, nm in enumerate(names):
+            ms, w = ctypes.c_double(), ctypes.c_double(); l, s = ctypes.c_longlong(), ctypes.c_longlong()
+            lib.tnb_profile_get(c, ctypes.byref(ms), ctypes.byref(w), ctypes.byref(l), ctypes.byref(s))
+            if l.value:
+                print("   %-14s %8.3f ms  launches %5d  scopes %5d  rate %.2f" % (nm, ms.value, l.value, s.value, w.value / max(ms.value, 1e-9) / 1e9))
+        lib.tnb_profile_enable(0)
