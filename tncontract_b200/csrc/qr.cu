@@ -15,6 +15,7 @@
 //     pipe (gemm.cu): W = V^H A2, W = T^H W, A2 -= V W.
 // Nominal flops (LAPACK model): 2(2mn^2 - 2/3 n^3) real, x4 complex.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -40,6 +41,7 @@ struct QrPanelArgs {
   int64_t m, ldw, ldv, ldt;
   int64_t j0;     // first column / diagonal row of the panel
   int jb;         // panel width (<= QR_NB)
+  int fast;       // try the CholeskyQR2 + Householder-reconstruction path first
   int rows_per;   // panel rows owned by each CTA of the cluster
   int pitch;      // shared-memory pitch of one panel column (elements)
 };
@@ -48,6 +50,116 @@ template <typename T> __device__ __forceinline__ T warp_sum_t(T v);
 template <> __device__ __forceinline__ double warp_sum_t<double>(double v) { return warp_sum(v); }
 template <> __device__ __forceinline__ cplx warp_sum_t<cplx>(cplx v) {
   return make_double2(warp_sum(v.x), warp_sum(v.y));
+}
+
+constexpr int QP = QR_NB + 4;  // pitch of the 32 x 32 matrices of the fast path (conflict-free DMMA fragments)
+
+// G (32 x 32, pitch QP) += this CTA's P^H P over K4 rows, on DMMA; 8 warps, two 8 x 8 tiles each.
+template <typename T>
+__device__ __forceinline__ void panel_gram(const T* P, int pitch, int K4, T* G, int warp, int lane) {
+  constexpr bool CPLX = (sizeof(T) == 16);
+  const int gq = lane >> 2, tq = lane & 3;
+  const int gm = warp >> 1, gn0 = (warp & 1) * 2;
+  double g[2][CPLX ? 4 : 2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int r = 0; r < (CPLX ? 4 : 2); ++r) g[j][r] = 0.0;
+  const T* pa = P + (gm * 8 + gq) * pitch + tq;
+  const T* pb0 = P + (gn0 * 8 + gq) * pitch + tq;
+  const T* pb1 = pb0 + 8 * pitch;
+#pragma unroll 4
+  for (int k0 = 0; k0 < K4; k0 += 4) {
+    const T av = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
+    if constexpr (CPLX) {
+      const double nay = -av.y;
+      dmma884(g[0][0], g[0][1], av.x, b0.x);
+      dmma884(g[0][2], g[0][3], av.x, b0.y);
+      dmma884(g[1][0], g[1][1], av.x, b1.x);
+      dmma884(g[1][2], g[1][3], av.x, b1.y);
+      dmma884(g[0][0], g[0][1], av.y, b0.y);
+      dmma884(g[0][2], g[0][3], nay, b0.x);
+      dmma884(g[1][0], g[1][1], av.y, b1.y);
+      dmma884(g[1][2], g[1][3], nay, b1.x);
+    } else {
+      dmma884(g[0][0], g[0][1], av, b0);
+      dmma884(g[1][0], g[1][1], av, b1);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int r = gm * 8 + gq, c = (gn0 + j) * 8 + 2 * tq;
+    if constexpr (CPLX) {
+      G[r * QP + c] = make_double2(g[j][0], g[j][2]);
+      G[r * QP + c + 1] = make_double2(g[j][1], g[j][3]);
+    } else {
+      G[r * QP + c] = g[j][0];
+      G[r * QP + c + 1] = g[j][1];
+    }
+  }
+}
+
+// In-place Cholesky G = R^H R of a 32 x 32 Hermitian matrix (pitch QP) by the whole CTA (256 threads):
+// on return the upper triangle holds R (real positive diagonal), invd[k] = 1 / R[k][k].  Returns false
+// (for every thread alike) when a pivot falls below `rel_floor` times its original diagonal entry --
+// the panel is then too ill-conditioned for CholeskyQR and the caller takes the Householder path.
+template <typename T>
+__device__ __forceinline__ bool panel_cholesky(T* G, T* invd, double* diag0, double rel_floor, int tid) {
+  typedef Num<T> N_;
+  const int i0 = (tid >> 5) * 4, k = tid & 31;  // this thread owns rows i0..i0+3 of column k
+  if (tid < QR_NB) diag0[tid] = N_::real(G[tid * QP + tid]);
+  bool ok = true;
+  for (int j = 0; j < QR_NB; ++j) {
+    __syncthreads();
+    const double piv = N_::real(G[j * QP + j]);
+    if (!(piv > rel_floor * diag0[j]) || !(piv > 0.0)) ok = false;
+    const double ipiv = 1.0 / piv;
+    const T rjk = G[j * QP + k];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int i = i0 + ii;
+      if (i > j && k >= i) {
+        const T f = N_::scale(N_::conj(G[j * QP + i]), ipiv);
+        G[i * QP + k] = N_::sub(G[i * QP + k], N_::mul(f, rjk));
+      }
+    }
+  }
+  __syncthreads();
+  // rows were kept unscaled (Schur complements): R[j][k] = G[j][k] / sqrt(G[j][j])
+  double rs[4];
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) rs[ii] = rsqrt(N_::real(G[(i0 + ii) * QP + i0 + ii]));
+  __syncthreads();
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) {
+    const int i = i0 + ii;
+    G[i * QP + k] = (k >= i) ? N_::scale(G[i * QP + k], rs[ii]) : N_::zero();
+    if (k == i) invd[i] = N_::from(rs[ii], 0.0);
+  }
+  __syncthreads();
+  return ok;
+}
+
+// rows r_begin.. of the slab (row r = P[0..31][r]) times the inverse of the upper triangular M (pitch QP,
+// invd[k] = 1 / M[k][k]): x M = p by forward substitution, one thread per row, everything in registers.
+template <typename T>
+__device__ __forceinline__ void panel_solve_rows(T* P, int pitch, int r_begin, int nrows, const T* M, const T* invd,
+                                                 int tid) {
+  typedef Num<T> N_;
+  for (int r = r_begin + tid; r < nrows; r += QR_THREADS) {
+    T x[QR_NB];
+#pragma unroll
+    for (int k = 0; k < QR_NB; ++k) x[k] = P[k * pitch + r];
+#pragma unroll
+    for (int k = 0; k < QR_NB; ++k) {
+      T acc = x[k];
+#pragma unroll
+      for (int q = 0; q < k; ++q) acc = N_::sub(acc, N_::mul(x[q], M[q * QP + k]));
+      x[k] = N_::mul(acc, invd[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < QR_NB; ++k) P[k * pitch + r] = x[k];
+  }
 }
 
 // Shared-memory layout (dynamic):
@@ -68,6 +180,8 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
   T* rowv = part + 2 * QR_NB;
   T* tau = rowv + 2 * QR_NB;
   T* Z = tau + QR_NB;
+  T* SA = Z + QR_NB * QR_NB;  // [QR_NB][QP]  fast path: Gram partial / top block of Q / L and U
+  T* SB = SA + QR_NB * QP;    // [QR_NB][QP]  fast path: Gram total -> Cholesky factor / copy of U
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int jb = a.jb;
@@ -84,6 +198,152 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
     P[c * a.pitch + r] = Wg[(a.j0 + r_lo + r) * a.ldw + a.j0 + c];
   }
   __syncthreads();
+
+  // =====================================================================================================
+  // Fast path (full 32-column panels whose first 32 rows sit in CTA 0): CholeskyQR2 + Householder
+  // reconstruction.  Q R = panel by two rounds of  G = P^H P (DMMA, one cluster reduction),  G = R^H R,
+  // P <- P R^-1;  then the Householder form of that Q (Ballard, Demmel, Grigori, Jacquelin, Nguyen,
+  // Solomonik, "Reconstructing Householder vectors from tall-skinny QR"):  Q - [S; 0] = L U without
+  // pivoting with S = -sign(Re diag) chosen on the fly (pivots have modulus >= 1),  V = L,
+  // T = -U S L1^-H,  R_householder = S R.  Six cluster barriers instead of one per column.  A panel whose
+  // Cholesky pivots fall below 1e-10 of the column norms (or a second pass that is not close to I) is
+  // too ill-conditioned for this and drops to the column-by-column Householder loop below, reloaded.
+  // =====================================================================================================
+  if (jb == QR_NB && a.rows_per >= QR_NB && a.fast) {
+    __shared__ double diag0[QR_NB];
+    __shared__ double sgn[QR_NB];
+    __shared__ T invd[QR_NB];
+    const int K4f = (nrows + 3) & ~3;
+    for (int i = tid; i < (K4f - nrows) * QR_NB; i += QR_THREADS) {
+      const int c = i / (K4f - nrows), r = nrows + (i - c * (K4f - nrows));
+      P[c * a.pitch + r] = N_::zero();
+    }
+    __syncthreads();
+    bool ok = true;
+    // ---- R_total (kept in Z, row-major pitch QR_NB) = R2 R1 -------------------------------------------
+    for (int pass = 0; pass < 2 && ok; ++pass) {
+      panel_gram<T>(P, a.pitch, K4f, SA, warp, lane);
+      cluster.sync();
+      for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+        const int i = idx / QR_NB, j = idx - i * QR_NB;
+        T sum = N_::zero();
+        for (int q = 0; q < C; ++q) sum = N_::add(sum, cluster.map_shared_rank(SA, q)[i * QP + j]);
+        SB[i * QP + j] = sum;
+      }
+      cluster.sync();  // every CTA has read every partial before SA is reused
+      ok = panel_cholesky<T>(SB, invd, diag0, pass == 0 ? 1e-10 : 0.25, tid);
+      if (!ok) break;
+      panel_solve_rows<T>(P, a.pitch, 0, nrows, SB, invd, tid);
+      if (pass == 0) {
+        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) Z[idx] = SB[(idx / QR_NB) * QP + (idx % QR_NB)];
+      } else {
+        // Z <- R2 Z (both upper triangular): thread (i, k) with a 32-term dot product
+        T newz[4];
+        const int i0 = (tid >> 5) * 4, k = tid & 31;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int i = i0 + ii;
+          T sum = N_::zero();
+          for (int q = i; q <= k; ++q) sum = N_::fma(SB[i * QP + q], Z[q * QR_NB + k], sum);
+          newz[ii] = sum;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) Z[(i0 + ii) * QR_NB + k] = newz[ii];
+      }
+      __syncthreads();
+    }
+    if (ok) {
+      // ---- Householder reconstruction.  CTA 0: LU of the top block with the sign choice --------------
+      if (crank == 0) {
+        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+          const int i = idx / QR_NB, j = idx - i * QR_NB;
+          SA[i * QP + j] = P[j * a.pitch + i];  // Q[i][j]
+        }
+        const int i = tid >> 3, k0 = (tid & 7) * 4;  // thread owns SA[i][k0..k0+3]
+        for (int j = 0; j < QR_NB; ++j) {
+          __syncthreads();
+          const T d = SA[j * QP + j];
+          const double sj = (N_::real(d) >= 0.0) ? -1.0 : 1.0;
+          const T piv = N_::sub(d, N_::from(sj, 0.0));
+          const double pn = 1.0 / N_::abs2(piv);
+          const T ipiv = N_::scale(N_::conj(piv), pn);
+          T lij = N_::zero(), rowj[4], mine[4];
+          if (i > j) lij = N_::mul(SA[i * QP + j], ipiv);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) { rowj[kk] = SA[j * QP + k0 + kk]; mine[kk] = SA[i * QP + k0 + kk]; }
+          __syncthreads();
+          if (i == j && tid == j * 8) { SA[j * QP + j] = piv; sgn[j] = sj; }
+          if (i > j) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const int k = k0 + kk;
+              if (k == j) SA[i * QP + k] = lij;
+              else if (k > j) SA[i * QP + k] = N_::sub(mine[kk], N_::mul(lij, rowj[kk]));
+            }
+          }
+        }
+        __syncthreads();
+      }
+      cluster.sync();  // U (upper triangle of CTA 0's SA) is final
+      {
+        const T* SA0 = cluster.map_shared_rank(SA, 0);
+        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+          const int i = idx / QR_NB, j = idx - i * QR_NB;
+          SB[i * QP + j] = (j >= i) ? SA0[i * QP + j] : N_::zero();
+        }
+        __syncthreads();
+        if (tid < QR_NB) {
+          const T u = SB[tid * QP + tid];
+          invd[tid] = N_::scale(N_::conj(u), 1.0 / N_::abs2(u));
+        }
+        __syncthreads();
+      }
+      cluster.sync();  // every CTA holds its own copy of U: CTA 0 may go on and exit whenever it likes
+      // ---- V: rows below the top block are q U^-1; the top block is L1 (unit lower triangular) ----------
+      const int top = (crank == 0) ? QR_NB : 0;
+      panel_solve_rows<T>(P, a.pitch, top, nrows, SB, invd, tid);
+      if (crank == 0) {
+        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+          const int i = idx / QR_NB, j = idx - i * QR_NB;
+          P[j * a.pitch + i] = (i > j) ? SA[i * QP + j] : (i == j ? N_::one() : N_::zero());
+        }
+        // R_householder = S R_total into the working matrix
+        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+          const int i = idx / QR_NB, k = idx - i * QR_NB;
+          if (k >= i) Wg[(a.j0 + i) * a.ldw + a.j0 + k] = N_::scale(Z[i * QR_NB + k], sgn[i]);
+        }
+        // T = -U S L1^-H:  row i of T solves  t L1^H = -(U S)[i][:]  (L1^H unit upper triangular)
+        if (tid < QR_NB) {
+          const int i = tid;
+          T t[QR_NB];
+#pragma unroll
+          for (int k = 0; k < QR_NB; ++k) {
+            T acc = (k >= i) ? N_::scale(SB[i * QP + k], -sgn[k]) : N_::zero();
+#pragma unroll
+            for (int q = 0; q < k; ++q) acc = N_::sub(acc, N_::mul(t[q], N_::conj(SA[k * QP + q])));
+            t[k] = acc;
+          }
+          T* Tg = reinterpret_cast<T*>(a.T);
+#pragma unroll
+          for (int k = 0; k < QR_NB; ++k) Tg[i * a.ldt + k] = (k >= i) ? t[k] : N_::zero();
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < nrows * jb; i += QR_THREADS) {
+        const int r = i / jb, c = i - r * jb;
+        Vg[(a.j0 + r_lo + r) * a.ldv + a.j0 + c] = P[c * a.pitch + r];
+      }
+      return;
+    }
+    // ill-conditioned panel: restore the slab and fall through to the Householder loop
+    __syncthreads();
+    for (int i = tid; i < nrows * jb; i += QR_THREADS) {
+      const int r = i / jb, c = i - r * jb;
+      P[c * a.pitch + r] = Wg[(a.j0 + r_lo + r) * a.ldw + a.j0 + c];
+    }
+    __syncthreads();
+  }
 
   // stage[r][c]: all CTAs' partial dots of the current column step, copied from DSMEM in ONE round trip
   T* stage = Z;  // QR_NB x QR_NB scratch: Z is only needed after the column loop (C <= 16 ranks <= QR_NB rows)
@@ -374,6 +634,9 @@ static inline unsigned blocks_for(int64_t n) {
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// kernel experiments: TNB_QR_FAST_PANEL=0 forces the column-by-column Householder panel
+static const int g_qr_fast_panel = (getenv("TNB_QR_FAST_PANEL") && atoi(getenv("TNB_QR_FAST_PANEL")) == 0) ? 0 : 1;
+
 constexpr int QR_NBO = 128;  // outer block: trailing updates and the explicit Q use K = 128 GEMMs
 
 struct QrLayout {
@@ -407,7 +670,7 @@ template <typename T>
 static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
   const int64_t mr = a.m - a.j0;
   // smallest cluster whose slabs fit in shared memory (cap 200 KB per CTA)
-  const size_t fixed = (size_t)(2 * QR_NB + 2 * QR_NB + QR_NB + QR_NB * QR_NB) * sizeof(T);
+  const size_t fixed = (size_t)(2 * QR_NB + 2 * QR_NB + QR_NB + QR_NB * QR_NB + 2 * QR_NB * QP) * sizeof(T);
   int C = 1;
   int rows_per = 0, pitch = 0;
   size_t smem = 0;
@@ -415,7 +678,7 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
     rows_per = (int)((mr + C - 1) / C);
     pitch = ((rows_per + 3) & ~3) + 1;  // odd (conflict-free transposing load), with room for the k4 zero padding
     smem = (size_t)QR_NB * pitch * sizeof(T) + fixed;
-    if (smem <= 200 * 1024) break;
+    if (smem <= 220 * 1024) break;
     if (C >= 16) return TNB_E_UNSUPPORTED;  // panel taller than 16 CTAs can hold
   }
   a.rows_per = rows_per;
@@ -424,8 +687,8 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
   static size_t configured_smem = 0;
   static bool nonportable = false;
   if (smem > configured_smem) {
-    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 1024)));
-    configured_smem = 201 * 1024;
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    configured_smem = 220 * 1024;
   }
   if (C > 8 && !nonportable) {
     TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -500,6 +763,7 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
       QrPanelArgs a;
       a.W = W; a.V = V; a.T = To + cb * QR_NBO + cb; a.ldt = QR_NBO;
       a.m = m; a.ldw = L.ldw; a.ldv = L.ldv; a.j0 = i0; a.jb = jb;
+      a.fast = g_qr_fast_panel;
       rc = launch_panel<T>(a, st);
       if (rc) return rc;
       const T* Vp = V + i0 * L.ldv + i0;
