@@ -113,7 +113,7 @@ __device__ __forceinline__ bool panel_cholesky(T* G, T* invd, double* diag0, dou
     __syncthreads();
     const double piv = N_::real(G[j * QP + j]);
     if (!(piv > rel_floor * diag0[j]) || !(piv > 0.0)) ok = false;
-    const double ipiv = 1.0 / piv;
+    const double ipiv = __drcp_rn(piv);
     const T rjk = G[j * QP + k];
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
@@ -133,8 +133,9 @@ __device__ __forceinline__ bool panel_cholesky(T* G, T* invd, double* diag0, dou
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii) {
     const int i = i0 + ii;
-    G[i * QP + k] = (k >= i) ? N_::scale(G[i * QP + k], rs[ii]) : N_::zero();
-    if (k == i) invd[i] = N_::from(rs[ii], 0.0);
+    T v = (k >= i) ? N_::scale(G[i * QP + k], rs[ii]) : N_::zero();
+    if (k == i) { v = N_::from(N_::real(v), 0.0); invd[i] = N_::from(rs[ii], 0.0); }  // exactly real diagonal
+    G[i * QP + k] = v;
   }
   __syncthreads();
   return ok;
@@ -142,9 +143,10 @@ __device__ __forceinline__ bool panel_cholesky(T* G, T* invd, double* diag0, dou
 
 // rows r_begin.. of the slab (row r = P[0..31][r]) times the inverse of the upper triangular M (pitch QP,
 // invd[k] = 1 / M[k][k]): x M = p by forward substitution, one thread per row, everything in registers.
+// (not inlined: the fully unrolled triangular recurrence is ~2500 instructions and is used three times)
 template <typename T>
-__device__ __forceinline__ void panel_solve_rows(T* P, int pitch, int r_begin, int nrows, const T* M, const T* invd,
-                                                 int tid) {
+__device__ __noinline__ void panel_solve_rows(T* P, int pitch, int r_begin, int nrows, const T* M, const T* invd,
+                                              int tid) {
   typedef Num<T> N_;
   for (int r = r_begin + tid; r < nrows; r += QR_THREADS) {
     T x[QR_NB];
@@ -227,7 +229,9 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
       for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
         const int i = idx / QR_NB, j = idx - i * QR_NB;
         T sum = N_::zero();
-        for (int q = 0; q < C; ++q) sum = N_::add(sum, cluster.map_shared_rank(SA, q)[i * QP + j]);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (q < C) sum = N_::add(sum, cluster.map_shared_rank(SA, q)[i * QP + j]);
         SB[i * QP + j] = sum;
       }
       cluster.sync();  // every CTA has read every partial before SA is reused
@@ -314,19 +318,21 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
           if (k >= i) Wg[(a.j0 + i) * a.ldw + a.j0 + k] = N_::scale(Z[i * QR_NB + k], sgn[i]);
         }
         // T = -U S L1^-H:  row i of T solves  t L1^H = -(U S)[i][:]  (L1^H unit upper triangular)
+        // (built in the upper triangle of SA, which is free once every CTA has copied U out of it;
+        //  the strictly lower triangle keeps L1)
         if (tid < QR_NB) {
           const int i = tid;
-          T t[QR_NB];
-#pragma unroll
-          for (int k = 0; k < QR_NB; ++k) {
-            T acc = (k >= i) ? N_::scale(SB[i * QP + k], -sgn[k]) : N_::zero();
-#pragma unroll
-            for (int q = 0; q < k; ++q) acc = N_::sub(acc, N_::mul(t[q], N_::conj(SA[k * QP + q])));
-            t[k] = acc;
+          for (int k = i; k < QR_NB; ++k) {
+            T acc = N_::scale(SB[i * QP + k], -sgn[k]);
+            for (int q = i; q < k; ++q) acc = N_::sub(acc, N_::mul(SA[i * QP + q], N_::conj(SA[k * QP + q])));
+            SA[i * QP + k] = acc;
           }
-          T* Tg = reinterpret_cast<T*>(a.T);
-#pragma unroll
-          for (int k = 0; k < QR_NB; ++k) Tg[i * a.ldt + k] = (k >= i) ? t[k] : N_::zero();
+        }
+        __syncthreads();
+        T* Tg = reinterpret_cast<T*>(a.T);
+        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+          const int i = idx / QR_NB, k = idx - i * QR_NB;
+          Tg[i * a.ldt + k] = (k >= i) ? SA[i * QP + k] : N_::zero();
         }
       }
       __syncthreads();
