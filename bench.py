@@ -156,10 +156,20 @@ def fp64_tensor_peak(torch, cplx):
 
 
 # ----------------------------------------------------------------------------- CPU arm
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is defined on ALL host cores."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def cpu_bulk_site_seconds(d, chi, D, reps):
     """The oracle's work for ONE bulk site of the sweep (chi=512, D=3: apply +
     consolidate, QR 3072x1536, R-absorb, SVD 1024x1536, truncation, V/S-absorb)."""
     from oracle import tn_oracle as o
+    _use_all_host_threads()
     rng = np.random.default_rng(0)
     m = chi * D
 

@@ -141,26 +141,93 @@ __device__ __forceinline__ bool panel_cholesky(T* G, T* invd, double* diag0, dou
   return ok;
 }
 
-// rows r_begin.. of the slab (row r = P[0..31][r]) times the inverse of the upper triangular M (pitch QP,
-// invd[k] = 1 / M[k][k]): x M = p by forward substitution, one thread per row, everything in registers.
-// (not inlined: the fully unrolled triangular recurrence is ~2500 instructions and is used three times)
+// Minv = M^-1 for a 32 x 32 upper triangular M (pitch QP) by recursive doubling, whole CTA (256 threads):
+// the diagonal first, then for block sizes b = 1, 2, .. 16 the off-diagonal blocks
+// X12 = -A^-1 B C^-1 of each pair of adjacent diagonal blocks.  `tmp` is a QR_NB x QP scratch matrix.
+// Serial depth ~ 2 * 31 complex multiply-adds instead of the ~500 of a column-by-column substitution.
 template <typename T>
-__device__ __noinline__ void panel_solve_rows(T* P, int pitch, int r_begin, int nrows, const T* M, const T* invd,
-                                              int tid) {
+__device__ __forceinline__ void panel_tri_inverse(const T* M, T* Minv, T* tmp, int tid) {
   typedef Num<T> N_;
-  for (int r = r_begin + tid; r < nrows; r += QR_THREADS) {
-    T x[QR_NB];
-#pragma unroll
-    for (int k = 0; k < QR_NB; ++k) x[k] = P[k * pitch + r];
-#pragma unroll
-    for (int k = 0; k < QR_NB; ++k) {
-      T acc = x[k];
-#pragma unroll
-      for (int q = 0; q < k; ++q) acc = N_::sub(acc, N_::mul(x[q], M[q * QP + k]));
-      x[k] = N_::mul(acc, invd[k]);
+  for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+    const int i = idx / QR_NB, j = idx - i * QR_NB;
+    T v = N_::zero();
+    if (i == j) {
+      const T u = M[i * QP + i];
+      v = N_::scale(N_::conj(u), 1.0 / N_::abs2(u));
     }
+    Minv[i * QP + j] = v;
+  }
+  __syncthreads();
+  for (int b = 1; b < QR_NB; b *= 2) {
+    // entries of all off-diagonal blocks at this level: (QR_NB / 2b) blocks of b x b = QR_NB * b / 2 entries
+    const int nent = QR_NB * b / 2;
+    // tmp = B Cinv   (B = M[s..s+b, s+b..s+2b), Cinv = Minv[s+b.., s+b..])
+    for (int e = tid; e < nent; e += QR_THREADS) {
+      const int blk = e / (b * b), r = (e / b) % b, c = e % b;
+      const int s0 = blk * 2 * b;
+      T sum = N_::zero();
+      for (int q = 0; q <= c; ++q) sum = N_::fma(M[(s0 + r) * QP + s0 + b + q], Minv[(s0 + b + q) * QP + s0 + b + c], sum);
+      tmp[(s0 + r) * QP + s0 + b + c] = sum;
+    }
+    __syncthreads();
+    // X12 = -Ainv tmp
+    for (int e = tid; e < nent; e += QR_THREADS) {
+      const int blk = e / (b * b), r = (e / b) % b, c = e % b;
+      const int s0 = blk * 2 * b;
+      T sum = N_::zero();
+      for (int q = r; q < b; ++q) sum = N_::fma(Minv[(s0 + r) * QP + s0 + q], tmp[(s0 + q) * QP + s0 + b + c], sum);
+      Minv[(s0 + r) * QP + s0 + b + c] = N_::sub(N_::zero(), sum);
+    }
+    __syncthreads();
+  }
+}
+
+// P (rows r_begin..nrows of the slab) <- P * B for a 32 x 32 matrix B (pitch QP), on DMMA.  Each warp owns
+// whole 8-row tiles: it reads every column of its rows before writing them back, so the product is in place.
+template <typename T>
+__device__ __forceinline__ void panel_right_mult(T* P, int pitch, int r_begin, int nrows, const T* B, int warp,
+                                                 int lane) {
+  constexpr bool CPLX = (sizeof(T) == 16);
+  typedef Num<T> N_;
+  const int gq = lane >> 2, tq = lane & 3;
+  for (int m0 = r_begin + warp * 8; m0 < nrows; m0 += QR_WARPS * 8) {
+    double acc[4][CPLX ? 4 : 2];
 #pragma unroll
-    for (int k = 0; k < QR_NB; ++k) P[k * pitch + r] = x[k];
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[nt][r] = 0.0;
+    const int row = m0 + gq;  // rows past nrows (< K4 <= pitch) read finite junk that is never stored
+#pragma unroll 2
+    for (int k0 = 0; k0 < QR_NB; k0 += 4) {
+      const T av = P[(k0 + tq) * pitch + row];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const T bv = B[(k0 + tq) * QP + nt * 8 + gq];
+        if constexpr (CPLX) {
+          dmma884(acc[nt][0], acc[nt][1], av.x, bv.x);
+          dmma884(acc[nt][2], acc[nt][3], av.x, bv.y);
+          dmma884(acc[nt][0], acc[nt][1], -av.y, bv.y);
+          dmma884(acc[nt][2], acc[nt][3], av.y, bv.x);
+        } else {
+          dmma884(acc[nt][0], acc[nt][1], av, bv);
+        }
+      }
+    }
+    __syncwarp();
+    if (row < nrows) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = nt * 8 + 2 * tq;
+        if constexpr (CPLX) {
+          P[c * pitch + row] = make_double2(acc[nt][0], acc[nt][2]);
+          P[(c + 1) * pitch + row] = make_double2(acc[nt][1], acc[nt][3]);
+        } else {
+          P[c * pitch + row] = acc[nt][0];
+          P[(c + 1) * pitch + row] = acc[nt][1];
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -183,7 +250,8 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
   T* tau = rowv + 2 * QR_NB;
   T* Z = tau + QR_NB;
   T* SA = Z + QR_NB * QR_NB;  // [QR_NB][QP]  fast path: Gram partial / top block of Q / L and U
-  T* SB = SA + QR_NB * QP;    // [QR_NB][QP]  fast path: Gram total -> Cholesky factor / copy of U
+  T* SB = SA + QR_NB * QP;    // [QR_NB][QP]  fast path: Gram total -> Cholesky factor / (U R2)^-1
+  T* SC = SB + QR_NB * QP;    // [QR_NB][QP]  fast path: scratch / top block of Q -> L and U
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int jb = a.jb;
@@ -208,7 +276,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
   // Solomonik, "Reconstructing Householder vectors from tall-skinny QR"):  Q - [S; 0] = L U without
   // pivoting with S = -sign(Re diag) chosen on the fly (pivots have modulus >= 1),  V = L,
   // T = -U S L1^-H,  R_householder = S R.  Six cluster barriers instead of one per column.  A panel whose
-  // Cholesky pivots fall below 1e-10 of the column norms (or a second pass that is not close to I) is
+  // Cholesky pivots fall below 1e-6 of the squared column norms (or a second pass that is not close to I) is
   // too ill-conditioned for this and drops to the column-by-column Householder loop below, reloaded.
   // =====================================================================================================
   if (jb == QR_NB && a.rows_per >= QR_NB && a.fast) {
@@ -222,7 +290,6 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
     }
     __syncthreads();
     bool ok = true;
-    // ---- R_total (kept in Z, row-major pitch QR_NB) = R2 R1 -------------------------------------------
     for (int pass = 0; pass < 2 && ok; ++pass) {
       panel_gram<T>(P, a.pitch, K4f, SA, warp, lane);
       cluster.sync();
@@ -235,13 +302,18 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
         SB[i * QP + j] = sum;
       }
       cluster.sync();  // every CTA has read every partial before SA is reused
-      ok = panel_cholesky<T>(SB, invd, diag0, pass == 0 ? 1e-10 : 0.25, tid);
+      ok = panel_cholesky<T>(SB, invd, diag0, pass == 0 ? 1e-6 : 0.25, tid);  // SB <- R (upper)
       if (!ok) break;
-      panel_solve_rows<T>(P, a.pitch, 0, nrows, SB, invd, tid);
       if (pass == 0) {
         for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) Z[idx] = SB[(idx / QR_NB) * QP + (idx % QR_NB)];
-      } else {
-        // Z <- R2 Z (both upper triangular): thread (i, k) with a 32-term dot product
+        panel_tri_inverse<T>(SB, SA, SC, tid);                 // SA <- R1^-1
+        panel_right_mult<T>(P, a.pitch, 0, nrows, SA, warp, lane);  // P <- P R1^-1 = Q1
+        __syncthreads();
+      }
+    }
+    if (ok) {
+      // R_total = R2 R1 (kept in Z, row-major pitch QR_NB): thread (i, k) with a dot product over q = i..k
+      {
         T newz[4];
         const int i0 = (tid >> 5) * 4, k = tid & 31;
 #pragma unroll
@@ -254,90 +326,100 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
         __syncthreads();
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) Z[(i0 + ii) * QR_NB + k] = newz[ii];
+        __syncthreads();
       }
-      __syncthreads();
-    }
-    if (ok) {
-      // ---- Householder reconstruction.  CTA 0: LU of the top block with the sign choice --------------
+      // ---- Householder reconstruction on CTA 0 (Q = Q1 R2^-1 is never formed below the top block) -----
       if (crank == 0) {
-        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
-          const int i = idx / QR_NB, j = idx - i * QR_NB;
-          SA[i * QP + j] = P[j * a.pitch + i];  // Q[i][j]
+        panel_tri_inverse<T>(SB, SA, SC, tid);  // SA <- R2^-1
+        {  // SC <- Q_top = Q1_top R2^-1
+          const int i = tid >> 3, k0 = (tid & 7) * 4;
+          T out[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int k = k0 + kk;
+            T sum = N_::zero();
+            for (int q = 0; q <= k; ++q) sum = N_::fma(P[q * a.pitch + i], SA[q * QP + k], sum);
+            out[kk] = sum;
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) SC[i * QP + k0 + kk] = out[kk];
         }
-        const int i = tid >> 3, k0 = (tid & 7) * 4;  // thread owns SA[i][k0..k0+3]
+        // LU of Q_top - S without pivoting, S_jj = -sign(Re pivot candidate) chosen on the fly
+        const int i = tid >> 3, k0 = (tid & 7) * 4;  // thread owns SC[i][k0..k0+3]
         for (int j = 0; j < QR_NB; ++j) {
           __syncthreads();
-          const T d = SA[j * QP + j];
+          const T d = SC[j * QP + j];
           const double sj = (N_::real(d) >= 0.0) ? -1.0 : 1.0;
           const T piv = N_::sub(d, N_::from(sj, 0.0));
-          const double pn = 1.0 / N_::abs2(piv);
-          const T ipiv = N_::scale(N_::conj(piv), pn);
+          const T ipiv = N_::scale(N_::conj(piv), __drcp_rn(N_::abs2(piv)));
           T lij = N_::zero(), rowj[4], mine[4];
-          if (i > j) lij = N_::mul(SA[i * QP + j], ipiv);
+          if (i > j) lij = N_::mul(SC[i * QP + j], ipiv);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) { rowj[kk] = SA[j * QP + k0 + kk]; mine[kk] = SA[i * QP + k0 + kk]; }
+          for (int kk = 0; kk < 4; ++kk) { rowj[kk] = SC[j * QP + k0 + kk]; mine[kk] = SC[i * QP + k0 + kk]; }
           __syncthreads();
-          if (i == j && tid == j * 8) { SA[j * QP + j] = piv; sgn[j] = sj; }
+          if (tid == j * 8) { SC[j * QP + j] = piv; sgn[j] = sj; }
           if (i > j) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const int k = k0 + kk;
-              if (k == j) SA[i * QP + k] = lij;
-              else if (k > j) SA[i * QP + k] = N_::sub(mine[kk], N_::mul(lij, rowj[kk]));
+              if (k == j) SC[i * QP + k] = lij;
+              else if (k > j) SC[i * QP + k] = N_::sub(mine[kk], N_::mul(lij, rowj[kk]));
             }
           }
         }
         __syncthreads();
-      }
-      cluster.sync();  // U (upper triangle of CTA 0's SA) is final
-      {
-        const T* SA0 = cluster.map_shared_rank(SA, 0);
-        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
-          const int i = idx / QR_NB, j = idx - i * QR_NB;
-          SB[i * QP + j] = (j >= i) ? SA0[i * QP + j] : N_::zero();
-        }
-        __syncthreads();
+        // T = -U S L1^-H: row i solves  t L1^H = -(U S)[i][:]  (L1^H unit upper triangular); built in the
+        // upper triangle of SA (R2^-1 is no longer needed)
         if (tid < QR_NB) {
-          const T u = SB[tid * QP + tid];
-          invd[tid] = N_::scale(N_::conj(u), 1.0 / N_::abs2(u));
-        }
-        __syncthreads();
-      }
-      cluster.sync();  // every CTA holds its own copy of U: CTA 0 may go on and exit whenever it likes
-      // ---- V: rows below the top block are q U^-1; the top block is L1 (unit lower triangular) ----------
-      const int top = (crank == 0) ? QR_NB : 0;
-      panel_solve_rows<T>(P, a.pitch, top, nrows, SB, invd, tid);
-      if (crank == 0) {
-        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
-          const int i = idx / QR_NB, j = idx - i * QR_NB;
-          P[j * a.pitch + i] = (i > j) ? SA[i * QP + j] : (i == j ? N_::one() : N_::zero());
-        }
-        // R_householder = S R_total into the working matrix
-        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
-          const int i = idx / QR_NB, k = idx - i * QR_NB;
-          if (k >= i) Wg[(a.j0 + i) * a.ldw + a.j0 + k] = N_::scale(Z[i * QR_NB + k], sgn[i]);
-        }
-        // T = -U S L1^-H:  row i of T solves  t L1^H = -(U S)[i][:]  (L1^H unit upper triangular)
-        // (built in the upper triangle of SA, which is free once every CTA has copied U out of it;
-        //  the strictly lower triangle keeps L1)
-        if (tid < QR_NB) {
-          const int i = tid;
-          for (int k = i; k < QR_NB; ++k) {
-            T acc = N_::scale(SB[i * QP + k], -sgn[k]);
-            for (int q = i; q < k; ++q) acc = N_::sub(acc, N_::mul(SA[i * QP + q], N_::conj(SA[k * QP + q])));
-            SA[i * QP + k] = acc;
+          const int ti = tid;
+          for (int k = ti; k < QR_NB; ++k) {
+            T acc = N_::scale(SC[ti * QP + k], -sgn[k]);
+            for (int q = ti; q < k; ++q) acc = N_::sub(acc, N_::mul(SA[ti * QP + q], N_::conj(SC[k * QP + q])));
+            SA[ti * QP + k] = acc;
           }
         }
         __syncthreads();
         T* Tg = reinterpret_cast<T*>(a.T);
         for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
-          const int i = idx / QR_NB, k = idx - i * QR_NB;
-          Tg[i * a.ldt + k] = (k >= i) ? SA[i * QP + k] : N_::zero();
+          const int r = idx / QR_NB, k = idx - r * QR_NB;
+          Tg[r * a.ldt + k] = (k >= r) ? SA[r * QP + k] : N_::zero();
+          // R_householder = S R_total into the working matrix
+          if (k >= r) Wg[(a.j0 + r) * a.ldw + a.j0 + k] = N_::scale(Z[r * QR_NB + k], sgn[r]);
+          // top block of V = L1 (unit lower triangular); Q1_top is no longer needed
+          P[k * a.pitch + r] = (r > k) ? SC[r * QP + k] : (r == k ? N_::one() : N_::zero());
         }
+        __syncthreads();
+        // SA <- M = U R2 (upper triangular), SB <- M^-1: rows below the top block are  Q1 M^-1
+        {
+          T out[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int k = k0 + kk;
+            T sum = N_::zero();
+            for (int q = i; q <= k; ++q) sum = N_::fma(SC[i * QP + q], SB[q * QP + k], sum);
+            out[kk] = sum;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) SA[i * QP + k0 + kk] = (k0 + kk >= i) ? out[kk] : N_::zero();
+          __syncthreads();
+        }
+        panel_tri_inverse<T>(SA, SB, SC, tid);
       }
+      cluster.sync();  // CTA 0's SB holds (U R2)^-1
+      if (crank != 0) {
+        const T* SB0 = cluster.map_shared_rank(SB, 0);
+        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+          const int r = idx / QR_NB, k = idx - r * QR_NB;
+          SA[r * QP + k] = SB0[r * QP + k];
+        }
+        __syncthreads();
+      }
+      cluster.sync();  // every CTA holds its own copy: CTA 0 may finish and exit whenever it likes
+      panel_right_mult<T>(P, a.pitch, crank == 0 ? QR_NB : 0, nrows, crank == 0 ? SB : SA, warp, lane);
       __syncthreads();
-      for (int i = tid; i < nrows * jb; i += QR_THREADS) {
-        const int r = i / jb, c = i - r * jb;
+      for (int idx = tid; idx < nrows * jb; idx += QR_THREADS) {
+        const int r = idx / jb, c = idx - r * jb;
         Vg[(a.j0 + r_lo + r) * a.ldv + a.j0 + c] = P[c * a.pitch + r];
       }
       return;
@@ -676,7 +758,7 @@ template <typename T>
 static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
   const int64_t mr = a.m - a.j0;
   // smallest cluster whose slabs fit in shared memory (cap 200 KB per CTA)
-  const size_t fixed = (size_t)(2 * QR_NB + 2 * QR_NB + QR_NB + QR_NB * QR_NB + 2 * QR_NB * QP) * sizeof(T);
+  const size_t fixed = (size_t)(2 * QR_NB + 2 * QR_NB + QR_NB + QR_NB * QR_NB + 3 * QR_NB * QP) * sizeof(T);
   int C = 1;
   int rows_per = 0, pitch = 0;
   size_t smem = 0;
