@@ -52,6 +52,10 @@ template <> __device__ __forceinline__ cplx warp_sum_t<cplx>(cplx v) {
   return make_double2(warp_sum(v.x), warp_sum(v.y));
 }
 
+// kernel experiments: phase timestamps of CTA 0 / thread 0 of the LAST panel launch (TNB_QR_FAST_PANEL=3)
+__device__ long long g_qr_dbg[32];
+#define QR_STAMP(k) do { if ((a.fast & 2) && crank == 0 && tid == 0) g_qr_dbg[k] = clock64(); } while (0)
+
 constexpr int QP = QR_NB + 4;  // pitch of the 32 x 32 matrices of the fast path (conflict-free DMMA fragments)
 
 // G (32 x 32, pitch QP) += this CTA's P^H P over K4 rows, on DMMA; 8 warps, two 8 x 8 tiles each.
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
   T* Wg = reinterpret_cast<T*>(a.W);
   T* Vg = reinterpret_cast<T*>(a.V);
 
+  QR_STAMP(0);
   // ---- load the slab (global rows are contiguous along c) --------------------------
   for (int i = tid; i < nrows * jb; i += QR_THREADS) {
     const int r = i / jb, c = i - r * jb;
@@ -290,25 +295,41 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
     }
     __syncthreads();
     bool ok = true;
+    QR_STAMP(1);
     for (int pass = 0; pass < 2 && ok; ++pass) {
       panel_gram<T>(P, a.pitch, K4f, SA, warp, lane);
+      QR_STAMP(2 + 6 * pass);
       cluster.sync();
-      for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
-        const int i = idx / QR_NB, j = idx - i * QR_NB;
-        T sum = N_::zero();
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          if (q < C) sum = N_::add(sum, cluster.map_shared_rank(SA, q)[i * QP + j]);
-        SB[i * QP + j] = sum;
+      // all-reduce over the cluster as reduce-scatter + all-gather through distributed shared memory: CTA c
+      // sums entries [c * per, (c + 1) * per) of all partials (in rank order: every entry is summed exactly
+      // once, so all CTAs end up with identical bits), then every CTA collects the 1024 sums.
+      {
+        const int per = (QR_NB * QR_NB) / C;  // C is a power of two <= 16
+        T* red = SC;                          // per (<= 1024) sums of this CTA
+        for (int e = tid; e < per; e += QR_THREADS) {
+          const int idx = crank * per + e, i = idx / QR_NB, j = idx - i * QR_NB;
+          T sum = N_::zero();
+          for (int q = 0; q < C; ++q) sum = N_::add(sum, cluster.map_shared_rank(SA, q)[i * QP + j]);
+          red[e] = sum;
+        }
+        cluster.sync();
+        for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+          const int i = idx / QR_NB, j = idx - i * QR_NB;
+          SB[i * QP + j] = cluster.map_shared_rank(red, idx / per)[idx % per];
+        }
       }
-      cluster.sync();  // every CTA has read every partial before SA is reused
+      cluster.sync();  // every CTA has read every partial / sum before SA and SC are reused
+      QR_STAMP(3 + 6 * pass);
       ok = panel_cholesky<T>(SB, invd, diag0, pass == 0 ? 1e-6 : 0.25, tid);  // SB <- R (upper)
+      QR_STAMP(4 + 6 * pass);
       if (!ok) break;
       if (pass == 0) {
         for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) Z[idx] = SB[(idx / QR_NB) * QP + (idx % QR_NB)];
         panel_tri_inverse<T>(SB, SA, SC, tid);                 // SA <- R1^-1
+        QR_STAMP(5);
         panel_right_mult<T>(P, a.pitch, 0, nrows, SA, warp, lane);  // P <- P R1^-1 = Q1
         __syncthreads();
+        QR_STAMP(6);
       }
     }
     if (ok) {
@@ -329,6 +350,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
         __syncthreads();
       }
       // ---- Householder reconstruction on CTA 0 (Q = Q1 R2^-1 is never formed below the top block) -----
+      QR_STAMP(12);
       if (crank == 0) {
         panel_tri_inverse<T>(SB, SA, SC, tid);  // SA <- R2^-1
         {  // SC <- Q_top = Q1_top R2^-1
@@ -344,30 +366,37 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) SC[i * QP + k0 + kk] = out[kk];
         }
+        QR_STAMP(13);
         // LU of Q_top - S without pivoting, S_jj = -sign(Re pivot candidate) chosen on the fly
         const int i = tid >> 3, k0 = (tid & 7) * 4;  // thread owns SC[i][k0..k0+3]
+        __shared__ T lu_ipiv[QR_NB];
         for (int j = 0; j < QR_NB; ++j) {
           __syncthreads();
+          // step j reads row j and column j and writes only rows > j, columns > j: one barrier per step.
+          // Column j keeps the unscaled a_ij; L[i][j] = a_ij / piv_j is formed after the loop.
           const T d = SC[j * QP + j];
           const double sj = (N_::real(d) >= 0.0) ? -1.0 : 1.0;
           const T piv = N_::sub(d, N_::from(sj, 0.0));
           const T ipiv = N_::scale(N_::conj(piv), __drcp_rn(N_::abs2(piv)));
-          T lij = N_::zero(), rowj[4], mine[4];
-          if (i > j) lij = N_::mul(SC[i * QP + j], ipiv);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) { rowj[kk] = SC[j * QP + k0 + kk]; mine[kk] = SC[i * QP + k0 + kk]; }
-          __syncthreads();
-          if (tid == j * 8) { SC[j * QP + j] = piv; sgn[j] = sj; }
+          if (tid == j * 8) { lu_ipiv[j] = ipiv; sgn[j] = sj; }
           if (i > j) {
+            const T lij = N_::mul(SC[i * QP + j], ipiv);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const int k = k0 + kk;
-              if (k == j) SC[i * QP + k] = lij;
-              else if (k > j) SC[i * QP + k] = N_::sub(mine[kk], N_::mul(lij, rowj[kk]));
+              if (k > j) SC[i * QP + k] = N_::sub(SC[i * QP + k], N_::mul(lij, SC[j * QP + k]));
             }
           }
         }
         __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = k0 + kk;
+          if (i > k) SC[i * QP + k] = N_::mul(SC[i * QP + k], lu_ipiv[k]);            // L
+          else if (i == k) SC[i * QP + k] = N_::sub(SC[i * QP + k], N_::from(sgn[k], 0.0));  // U diagonal = pivot
+        }
+        __syncthreads();
+        QR_STAMP(14);
         // T = -U S L1^-H: row i solves  t L1^H = -(U S)[i][:]  (L1^H unit upper triangular); built in the
         // upper triangle of SA (R2^-1 is no longer needed)
         if (tid < QR_NB) {
@@ -389,6 +418,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
           P[k * a.pitch + r] = (r > k) ? SC[r * QP + k] : (r == k ? N_::one() : N_::zero());
         }
         __syncthreads();
+        QR_STAMP(15);
         // SA <- M = U R2 (upper triangular), SB <- M^-1: rows below the top block are  Q1 M^-1
         {
           T out[4];
@@ -405,6 +435,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
           __syncthreads();
         }
         panel_tri_inverse<T>(SA, SB, SC, tid);
+        QR_STAMP(16);
       }
       cluster.sync();  // CTA 0's SB holds (U R2)^-1
       if (crank != 0) {
@@ -416,12 +447,15 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(QrPanelArgs a) {
         __syncthreads();
       }
       cluster.sync();  // every CTA holds its own copy: CTA 0 may finish and exit whenever it likes
+      QR_STAMP(17);
       panel_right_mult<T>(P, a.pitch, crank == 0 ? QR_NB : 0, nrows, crank == 0 ? SB : SA, warp, lane);
       __syncthreads();
+      QR_STAMP(18);
       for (int idx = tid; idx < nrows * jb; idx += QR_THREADS) {
         const int r = idx / jb, c = idx - r * jb;
         Vg[(a.j0 + r_lo + r) * a.ldv + a.j0 + c] = P[c * a.pitch + r];
       }
+      QR_STAMP(19);
       return;
     }
     // ill-conditioned panel: restore the slab and fall through to the Householder loop
@@ -723,7 +757,7 @@ static inline unsigned blocks_for(int64_t n) {
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // kernel experiments: TNB_QR_FAST_PANEL=0 forces the column-by-column Householder panel
-static const int g_qr_fast_panel = (getenv("TNB_QR_FAST_PANEL") && atoi(getenv("TNB_QR_FAST_PANEL")) == 0) ? 0 : 1;
+static const int g_qr_fast_panel = getenv("TNB_QR_FAST_PANEL") ? atoi(getenv("TNB_QR_FAST_PANEL")) : 1;
 
 constexpr int QR_NBO = 128;  // outer block: trailing updates and the explicit Q use K = 128 GEMMs
 
@@ -940,4 +974,11 @@ extern "C" int tnb_qr(int dtype, int64_t m, int64_t n, const void* A, int64_t ld
   if (!A || !ws) return TNB_E_ARG;
   if (ws_bytes < tnb::qr_workspace(dtype, m, n)) return TNB_E_WORKSPACE;
   return tnb::qr(dtype, m, n, A, lda, Q, R, ws, 1, nullptr, (cudaStream_t)stream);
+}
+
+// kernel experiments: phase timestamps (clock64) of the last fast-path panel, see QR_STAMP
+extern "C" int tnb_debug_qr_stamps(long long* out, int n) {
+  if (!out || n <= 0 || n > 32) return TNB_E_ARG;
+  TNB_CUDA_CHECK(cudaMemcpyFromSymbol(out, tnb::g_qr_dbg, (size_t)n * sizeof(long long)));
+  return 0;
 }

@@ -237,9 +237,11 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   // ---- partial Gram matrix of this CTA's Xt chunks on the FP64 tensor pipe (DMMA.8x8x4) ----------
   // G[p][q] = sum_c conj(P[p][c]) P[q][c]: 4 x 4 tiles of 8 x 8, one per warp; both fragments are rows
   // of P with c (= k) contiguous, lane (gq, tq) holds element [row0 + gq][k0 + tq].
-  double g[CPLX ? 4 : 2];
+  // two interleaved accumulator sets: DMMA has a long dependent-issue latency and each set is only a
+  // 2-deep chain per k-step
+  double g[CPLX ? 4 : 2], h[CPLX ? 4 : 2];
 #pragma unroll
-  for (int r = 0; r < (CPLX ? 4 : 2); ++r) g[r] = 0.0;
+  for (int r = 0; r < (CPLX ? 4 : 2); ++r) { g[r] = 0.0; h[r] = 0.0; }
   const int gm = warp >> 2, gn = warp & 3;
   int resident = -1;
   for (int gch = crank; gch < a.nx; gch += S) {
@@ -252,20 +254,27 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
 #ifdef TNB_EXP_SKIP_GRAM
     for (int k0 = 0; k0 < 4; k0 += 4) {
 #else
-#pragma unroll 8
-    for (int k0 = 0; k0 < CH; k0 += 4) {
+#pragma unroll 4
+    for (int k0 = 0; k0 < CH; k0 += 8) {
 #endif
-      const T av = pa[k0], bv = pb[k0];
+      const T av = pa[k0], bv = pb[k0], av2 = pa[k0 + 4], bv2 = pb[k0 + 4];
       if constexpr (CPLX) {
         dmma884(g[0], g[1], av.x, bv.x);
         dmma884(g[2], g[3], av.x, bv.y);
+        dmma884(h[0], h[1], av2.x, bv2.x);
+        dmma884(h[2], h[3], av2.x, bv2.y);
         dmma884(g[0], g[1], av.y, bv.y);
         dmma884(g[2], g[3], -av.y, bv.x);
+        dmma884(h[0], h[1], av2.y, bv2.y);
+        dmma884(h[2], h[3], -av2.y, bv2.x);
       } else {
         dmma884(g[0], g[1], av, bv);
+        dmma884(h[0], h[1], av2, bv2);
       }
     }
   }
+#pragma unroll
+  for (int r = 0; r < (CPLX ? 4 : 2); ++r) g[r] += h[r];
   {
     const int r = gm * 8 + gq, c = gn * 8 + 2 * tq;
     if constexpr (CPLX) {
