@@ -150,6 +150,9 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// waits only until the shared-memory SOURCE of every committed bulk store has been read (the buffer may
+// be reused, the CTA may exit); the global writes themselves complete by the end of the grid at the latest
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

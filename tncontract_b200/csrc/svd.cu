@@ -27,8 +27,8 @@
 //     partials are summed through distributed shared memory (two cluster
 //     barriers, identical summation order everywhere, so every CTA holds the
 //     same bits);
-//   * every CTA runs the same parallel-ordered two-sided Jacobi sweep on the
-//     Gram matrix in shared memory (31 steps of 16 disjoint rotations,
+//   * every CTA runs the same parallel-ordered two-sided Jacobi steps on the
+//     Gram matrix in shared memory (16 or 15 steps of 16 disjoint rotations,
 //     thread (a, b) owns the 2 x 2 block between rotation pairs a and b), which
 //     yields the 32 x 32 unitary W of accumulated rotations; the rotation
 //     angles are exactly those of one-sided Jacobi on the columns;
@@ -63,6 +63,16 @@ constexpr int JT = 512;      // threads per CTA: 2 x (JP/2)^2 -- G blocks on the
 constexpr int JGP = JP + 4;  // pitch of the small matrices in shared memory (= 4 mod 8: conflict-free DMMA fragments)
 constexpr int JPAD = 4;      // panel pitch = CH + JPAD for the same reason
 constexpr int MAX_SWEEPS = 60;
+constexpr int GRAM_TILES = 10;  // upper 8 x 8 tiles of the 4 x 4 tile grid of a JP x JP Hermitian matrix
+constexpr int GRAM_UPW = 5;     // Gram work units (tile, eighth of a chunk) per warp: 10 * 8 / 16
+
+// t-th upper tile (row-major over gm <= gn) of the 4 x 4 tile grid
+__device__ __forceinline__ void upper_tile(int t, int& gm, int& gn) {
+  if (t < 4) { gm = 0; gn = t; }
+  else if (t < 7) { gm = 1; gn = t - 3; }
+  else if (t < 9) { gm = 2; gn = t - 5; }
+  else { gm = 3; gn = 3; }
+}
 
 struct JacobiFlags {
   unsigned int state;  // rotation flags of the sweep in flight (see jacobi_finish_sweep_kernel)
@@ -111,12 +121,10 @@ template <typename T> struct Rot { double c; T sp; };
 // The pair counts as converged when |g|^2 <= tol2 alpha beta; bit 0 of `state` records a rotation,
 // bit 1 one whose squared cosine exceeded 1e-20 (see jacobi_finish_sweep_kernel).
 template <typename T>
-__device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol2, unsigned& state) {
+__device__ __forceinline__ Rot<T> make_rot_vals(double alpha, double beta, T gam, double tol2, unsigned& state) {
   typedef Num<T> N_;
   Rot<T> r;
   r.c = 1.0; r.sp = N_::zero();
-  const double alpha = N_::real(G[p * JGP + p]), beta = N_::real(G[q * JGP + q]);
-  const T gam = G[p * JGP + q];
   const double ag2 = N_::abs2(gam);
   const double ab = alpha * beta;
   if (ab > 0.0 && ag2 > tol2 * ab) {
@@ -129,6 +137,11 @@ __device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol2
     r.sp = N_::scale(gam, copysign(0.5 * rh * rc, tau));
   }
   return r;
+}
+template <typename T>
+__device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol2, unsigned& state) {
+  typedef Num<T> N_;
+  return make_rot_vals<T>(N_::real(G[p * JGP + p]), N_::real(G[q * JGP + q]), G[p * JGP + q], tol2, state);
 }
 
 template <typename T> __device__ __forceinline__ T shfl_t(T v, int src);
@@ -145,12 +158,28 @@ __device__ __forceinline__ cplx rot_mix(double c, cplx x, cplx s, cplx y) {
   return make_double2(fma(c, x.x, fma(s.x, y.x, -(s.y * y.y))), fma(c, x.y, fma(s.x, y.y, s.y * y.x)));
 }
 
+// Entry (r, k) of B' = J_a^H B J_b for the 2 x 2 block B = [[b00, b01], [b10, b11]]
+// (J = [[c, sp], [-conj(sp), c]]); the same operation order as the full block update of the round kernel.
+template <typename T>
+__device__ __forceinline__ T rotated_entry(T b00, T b01, T b10, T b11, const Rot<T>& Ra, const Rot<T>& Rb, int r, int k) {
+  typedef Num<T> N_;
+  const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));
+  T t0, t1;
+  if (k == 0) { t0 = rot_mix(Rb.c, b00, msb, b01); t1 = rot_mix(Rb.c, b10, msb, b11); }
+  else { t0 = rot_mix(Rb.c, b01, Rb.sp, b00); t1 = rot_mix(Rb.c, b11, Rb.sp, b10); }
+  if (r == 0) return rot_mix(Ra.c, t0, N_::sub(N_::zero(), Ra.sp), t1);
+  return rot_mix(Ra.c, t1, N_::conj(Ra.sp), t0);
+}
+
 // Shared memory: P[JP][CH+JPAD] | G[2][JP][JGP] | W[2][JP][JGP]  (the cluster-reduction partials live in W's space)
 template <typename T>
 __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   typedef Num<T> N_;
   constexpr bool CPLX = (sizeof(T) == 16);
   if (a.flags->converged) return;  // uniform over the whole grid
+#ifdef TNB_EXP_EMPTY
+  return;  // kernel experiments: launch cost of this grid / cluster / shared-memory configuration alone
+#endif
   cg::cluster_group cluster = cg::this_cluster();
   const int S = a.S;
   const int crank = (int)cluster.block_rank();
@@ -172,6 +201,11 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   //   diag  round: two independent 16-player tournaments, one inside each block       (15 steps)
   // One diag round plus nblk - 1 cross rounds rotate every column pair exactly once per sweep.
   __shared__ unsigned char s_rr[JB][JP / 2][2];
+  // s_pos[step][i] = 2 * (rotation pair holding panel column i in that step) + (1 if i is the larger one)
+  __shared__ unsigned char s_pos[JB][JP];
+  // s_nxt[step][a]: for rotation pair a of step + 1, the two pairs of `step` its columns come from and
+  // on which side: byte 0 = pair of the smaller column, byte 1 = its side, byte 2 / 3 = same for the larger
+  __shared__ unsigned int s_nxt[JB][JP / 2];
   const int nsteps = a.diag ? JB - 1 : JB;
   if (tid < nsteps * (JP / 2)) {
     const int st_ = tid / (JP / 2), pr_ = tid % (JP / 2);
@@ -183,8 +217,17 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
       x = pr_;
       y = JB + ((pr_ + st_) & (JB - 1));
     }
-    s_rr[st_][pr_][0] = (unsigned char)(x < y ? x : y);
-    s_rr[st_][pr_][1] = (unsigned char)(x < y ? y : x);
+    const int lo_ = x < y ? x : y, hi_ = x < y ? y : x;
+    s_rr[st_][pr_][0] = (unsigned char)lo_;
+    s_rr[st_][pr_][1] = (unsigned char)hi_;
+    s_pos[st_][lo_] = (unsigned char)(2 * pr_);
+    s_pos[st_][hi_] = (unsigned char)(2 * pr_ + 1);
+  }
+  __syncthreads();
+  if (tid < (nsteps - 1) * (JP / 2)) {
+    const int st_ = tid / (JP / 2), pr_ = tid % (JP / 2);
+    const unsigned p1 = s_pos[st_][s_rr[st_ + 1][pr_][0]], p2 = s_pos[st_][s_rr[st_ + 1][pr_][1]];
+    s_nxt[st_][pr_] = (p1 >> 1) | ((p1 & 1u) << 8) | ((p2 >> 1) << 16) | ((p2 & 1u) << 24);
   }
   T* Xg = reinterpret_cast<T*>(a.X);
   T* Vg = reinterpret_cast<T*>(a.V);
@@ -235,62 +278,98 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   };
 
   // ---- partial Gram matrix of this CTA's Xt chunks on the FP64 tensor pipe (DMMA.8x8x4) ----------
-  // G[p][q] = sum_c conj(P[p][c]) P[q][c]: 4 x 4 tiles of 8 x 8, one per warp; both fragments are rows
-  // of P with c (= k) contiguous, lane (gq, tq) holds element [row0 + gq][k0 + tq].
-  // two interleaved accumulator sets: DMMA has a long dependent-issue latency and each set is only a
-  // 2-deep chain per k-step
-  double g[CPLX ? 4 : 2], h[CPLX ? 4 : 2];
+  // G[p][q] = sum_c conj(P[p][c]) P[q][c] is Hermitian: only the 10 upper 8 x 8 tiles of the 4 x 4 tile
+  // grid are formed.  Work unit = (tile, eighth of the chunk); the 80 units are dealt 5 per warp, so a
+  // warp touches at most two tiles (accumulator sets A and B, kept across the chunks of this CTA).
+  // Both fragments are rows of P with c (= k) contiguous, lane (gq, tq) holds element [row0 + gq][k0 + tq].
+  // Complex products use the 3-multiplication form (3 DMMAs per tile and k-step instead of 4):
+  //   P1 = ar br, P2 = ai bi, P3 = (ar + ai)(br - bi):  re = P1 + P2,  im = P1 - P2 - P3.
+  constexpr int NACC = CPLX ? 6 : 2;
+  double accA[NACC], accB[NACC];
 #pragma unroll
-  for (int r = 0; r < (CPLX ? 4 : 2); ++r) { g[r] = 0.0; h[r] = 0.0; }
-  const int gm = warp >> 2, gn = warp & 3;
+  for (int r = 0; r < NACC; ++r) { accA[r] = 0.0; accB[r] = 0.0; }
+  const int u0 = warp * GRAM_UPW;
+  const int tA = u0 >> 3, sA0 = u0 & 7;
+  const int nA = (8 - sA0 < GRAM_UPW) ? (8 - sA0) : GRAM_UPW;  // units of this warp in tile tA
+  const int nB = GRAM_UPW - nA;                                // ... and in tile tA + 1 (from its slice 0)
+  int gmA, gnA, gmB, gnB;
+  upper_tile(tA, gmA, gnA);
+  upper_tile(nB > 0 ? tA + 1 : tA, gmB, gnB);
+  const int SL = CH >> 3;  // chunk elements per unit (CH >= 32: a multiple of the DMMA k = 4)
+  auto gram_units = [&](double (&acc)[NACC], int gm, int gn, int kbeg, int klen) {
+    const T* pa = P + (gm * 8 + gq) * pitch + tq + kbeg;
+    const T* pb = P + (gn * 8 + gq) * pitch + tq + kbeg;
+#ifdef TNB_EXP_SKIP_GRAM
+    klen = 4;
+#endif
+#pragma unroll 4
+    for (int k0 = 0; k0 < klen; k0 += 4) {
+      const T av = pa[k0], bv = pb[k0];
+      if constexpr (CPLX) {
+        dmma884(acc[0], acc[1], av.x, bv.x);
+        dmma884(acc[2], acc[3], av.y, bv.y);
+        dmma884(acc[4], acc[5], av.x + av.y, bv.x - bv.y);
+      } else {
+        dmma884(acc[0], acc[1], av, bv);
+      }
+    }
+  };
   int resident = -1;
   for (int gch = crank; gch < a.nx; gch += S) {
     __syncthreads();
     load_chunk(gch);
     __syncthreads();
     resident = gch;
-    const T* pa = P + (gm * 8 + gq) * pitch + tq;
-    const T* pb = P + (gn * 8 + gq) * pitch + tq;
-#ifdef TNB_EXP_SKIP_GRAM
-    for (int k0 = 0; k0 < 4; k0 += 4) {
-#else
-#pragma unroll 4
-    for (int k0 = 0; k0 < CH; k0 += 8) {
-#endif
-      const T av = pa[k0], bv = pb[k0], av2 = pa[k0 + 4], bv2 = pb[k0 + 4];
-      if constexpr (CPLX) {
-        dmma884(g[0], g[1], av.x, bv.x);
-        dmma884(g[2], g[3], av.x, bv.y);
-        dmma884(h[0], h[1], av2.x, bv2.x);
-        dmma884(h[2], h[3], av2.x, bv2.y);
-        dmma884(g[0], g[1], av.y, bv.y);
-        dmma884(g[2], g[3], -av.y, bv.x);
-        dmma884(h[0], h[1], av2.y, bv2.y);
-        dmma884(h[2], h[3], -av2.y, bv2.x);
-      } else {
-        dmma884(g[0], g[1], av, bv);
-        dmma884(h[0], h[1], av2, bv2);
-      }
-    }
+    gram_units(accA, gmA, gnA, sA0 * SL, nA * SL);
+    if (nB > 0) gram_units(accB, gmB, gnB, 0, nB * SL);
   }
-#pragma unroll
-  for (int r = 0; r < (CPLX ? 4 : 2); ++r) g[r] += h[r];
+  // per-warp partial tiles -> slots (in the space of G), summed per tile in a fixed order -> Gpart
+  T* slots = G;  // [16 warps][2][64]
   {
-    const int r = gm * 8 + gq, c = gn * 8 + 2 * tq;
-    if constexpr (CPLX) {
-      Gpart[r * JGP + c] = make_double2(g[0], g[2]);
-      Gpart[r * JGP + c + 1] = make_double2(g[1], g[3]);
-    } else {
-      Gpart[r * JGP + c] = g[0];
-      Gpart[r * JGP + c + 1] = g[1];
-    }
+    auto flush = [&](const double (&acc)[NACC], int j) {
+      T* dst = slots + (warp * 2 + j) * 64 + gq * 8 + 2 * tq;
+      if constexpr (CPLX) {
+        dst[0] = make_double2(acc[0] + acc[2], acc[0] - acc[2] - acc[4]);
+        dst[1] = make_double2(acc[1] + acc[3], acc[1] - acc[3] - acc[5]);
+      } else {
+        dst[0] = acc[0];
+        dst[1] = acc[1];
+      }
+    };
+    flush(accA, 0);
+    if (nB > 0) flush(accB, 1);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < GRAM_TILES * 64; idx += JT) {
+    const int t = idx >> 6, e = idx & 63;
+    int gm, gn;
+    upper_tile(t, gm, gn);
+    T sum = N_::zero();
+    for (int w = (8 * t) / GRAM_UPW; w <= (8 * t + 7) / GRAM_UPW; ++w)
+      sum = N_::add(sum, slots[(w * 2 + ((((w * GRAM_UPW) >> 3) == t) ? 0 : 1)) * 64 + e]);
+    Gpart[(gm * 8 + (e >> 3)) * JGP + gn * 8 + (e & 7)] = sum;
   }
   cluster.sync();
-  for (int idx = tid; idx < JP * JP; idx += JT) {
-    const int i = idx / JP, j = idx - i * JP;
-    T sum = N_::zero();
-    for (int q = 0; q < S; ++q) sum = N_::add(sum, cluster.map_shared_rank(Gpart, q)[i * JGP + j]);
-    G[i * JGP + j] = sum;
+  // sum of the cluster's partials (same order in every CTA: identical bits everywhere), mirrored into
+  // the lower triangle; the diagonal is real
+  for (int idx = tid; idx < GRAM_TILES * 64; idx += JT) {
+    const int t = idx >> 6, e = idx & 63;
+    int gm, gn;
+    upper_tile(t, gm, gn);
+    const int i = gm * 8 + (e >> 3), j = gn * 8 + (e & 7);
+    if (i > j) continue;
+    T part[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) part[q] = (q < S) ? cluster.map_shared_rank(Gpart, q)[i * JGP + j] : N_::zero();
+    T sum = part[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) sum = N_::add(sum, part[q]);
+    if (i == j) {
+      G[i * JGP + i] = N_::from(N_::real(sum), 0.0);
+    } else {
+      G[i * JGP + j] = sum;
+      G[j * JGP + i] = N_::conj(sum);
+    }
   }
   cluster.sync();  // all remote reads done before any CTA overwrites its partials (or exits)
   for (int idx = tid; idx < JP * JP; idx += JT) {
@@ -300,31 +379,58 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   __syncthreads();
 
   // ---- parallel-ordered Jacobi rotations on G, accumulated in W --------------------------------------
-  // 16 (cross round) or 15 (diag round) steps of 16 disjoint rotations.  Threads 0..255: thread (ta, tb) owns the 2 x 2 block of G
-  // between rotation pairs ta and tb (B' = J_a^H B J_b).  Threads 256..511: rows 2ta, 2ta+1 of W times
-  // J_b.  Every thread builds the rotation of pair tb = lane & 15; the one of pair ta comes from lane ta.
-  // G and W ping-pong between two buffers, so a step needs a single barrier.
-  const int role = tid >> 8, ta = (tid & 255) >> 4, tb = tid & 15;
+  // 16 (cross round) or 15 (diag round) steps of 16 disjoint rotations, one barrier per step:
+  //   warps 0..7  : thread (ta, tb) owns the 2 x 2 block of G between rotation pairs ta and tb
+  //                 (B' = J_a^H B J_b);
+  //   warps 8..14 : W' = W J_b on rows 2ta, 2ta+1 (256 tasks on 224 threads, warp 8 takes two);
+  //   warp 15     : builds the rotations of step s + 1 WHILE the others apply those of step s: the three
+  //                 entries of G^(s+1) a rotation needs follow from three 2 x 2 blocks of G^(s) and the
+  //                 two rotations of step s that touch its columns (rotated_entry).  The long dependent
+  //                 chain of make_rot (two rsqrt) is thereby off the critical path of the step.
+  // G and W ping-pong between two buffers, the rotations between s_rc/s_rsp[0] and [1].
+  constexpr int ROTW = JT / 32 - 1;
+  const int ta = (tid & 255) >> 4, tb = tid & 15;
   const double tol2 = a.tol * a.tol;
   unsigned state = 0;
-#ifdef TNB_EXP_SKIP_EIGEN
-  for (int step = 0; step < 0; ++step) {
-#else
+  __shared__ double s_rc[2][JP / 2];
+  __shared__ T s_rsp[2][JP / 2];
+#ifndef TNB_EXP_SKIP_EIGEN
+  if (warp == ROTW && lane < JP / 2) {
+    const Rot<T> r = make_rot<T>(G, s_rr[0][lane][0], s_rr[0][lane][1], tol2, state);
+    s_rc[0][lane] = r.c;
+    s_rsp[0][lane] = r.sp;
+  }
+  __syncthreads();
   for (int step = 0; step < nsteps; ++step) {
-#endif
-    const T* Gc = G + (step & 1) * (JP * JGP);
-    T* Gn = G + ((step & 1) ^ 1) * (JP * JGP);
-    const T* Wc = W + (step & 1) * (JP * JGP);
-    T* Wn = W + ((step & 1) ^ 1) * (JP * JGP);
-    const int pa = s_rr[step][ta][0], qa = s_rr[step][ta][1];
-    const int pb = s_rr[step][tb][0], qb = s_rr[step][tb][1];
-    const Rot<T> Rb = make_rot<T>(Gc, pb, qb, tol2, state);
-    const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));  // -conj(sp_b)
-    if (role == 0) {
+    const int cur = step & 1;
+    const T* Gc = G + cur * (JP * JGP);
+    T* Gn = G + (cur ^ 1) * (JP * JGP);
+    const T* Wc = W + cur * (JP * JGP);
+    T* Wn = W + (cur ^ 1) * (JP * JGP);
+    if (warp == ROTW) {
+      if (lane < JP / 2 && step + 1 < nsteps) {
+        const unsigned nx_ = s_nxt[step][lane];
+        const int a1 = nx_ & 0xff, r1 = (nx_ >> 8) & 1, a2 = (nx_ >> 16) & 0xff, r2 = (nx_ >> 24) & 1;
+        const int p1 = s_rr[step][a1][0], q1 = s_rr[step][a1][1];
+        const int p2 = s_rr[step][a2][0], q2 = s_rr[step][a2][1];
+        Rot<T> R1, R2;
+        R1.c = s_rc[cur][a1]; R1.sp = s_rsp[cur][a1];
+        R2.c = s_rc[cur][a2]; R2.sp = s_rsp[cur][a2];
+        const T al = rotated_entry<T>(Gc[p1 * JGP + p1], Gc[p1 * JGP + q1], Gc[q1 * JGP + p1], Gc[q1 * JGP + q1], R1, R1, r1, r1);
+        const T be = rotated_entry<T>(Gc[p2 * JGP + p2], Gc[p2 * JGP + q2], Gc[q2 * JGP + p2], Gc[q2 * JGP + q2], R2, R2, r2, r2);
+        const T ga = rotated_entry<T>(Gc[p1 * JGP + p2], Gc[p1 * JGP + q2], Gc[q1 * JGP + p2], Gc[q1 * JGP + q2], R1, R2, r1, r2);
+        const Rot<T> r = make_rot_vals<T>(N_::real(al), N_::real(be), ga, tol2, state);
+        s_rc[cur ^ 1][lane] = r.c;
+        s_rsp[cur ^ 1][lane] = r.sp;
+      }
+    } else if (warp < 8) {
+      const int pa = s_rr[step][ta][0], qa = s_rr[step][ta][1];
+      const int pb = s_rr[step][tb][0], qb = s_rr[step][tb][1];
+      Rot<T> Ra, Rb;
+      Ra.c = s_rc[cur][ta]; Ra.sp = s_rsp[cur][ta];
+      Rb.c = s_rc[cur][tb]; Rb.sp = s_rsp[cur][tb];
+      const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));  // -conj(sp_b)
       const T b00 = Gc[pa * JGP + pb], b01 = Gc[pa * JGP + qb], b10 = Gc[qa * JGP + pb], b11 = Gc[qa * JGP + qb];
-      Rot<T> Ra;
-      Ra.c = __shfl_sync(0xffffffffu, Rb.c, ta);
-      Ra.sp = shfl_t<T>(Rb.sp, ta);
       // T1 = B J_b:  T1[:,0] = c B[:,0] - conj(sp) B[:,1],  T1[:,1] = sp B[:,0] + c B[:,1]
       const T t00 = rot_mix(Rb.c, b00, msb, b01), t01 = rot_mix(Rb.c, b01, Rb.sp, b00);
       const T t10 = rot_mix(Rb.c, b10, msb, b11), t11 = rot_mix(Rb.c, b11, Rb.sp, b10);
@@ -340,16 +446,25 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
       }
       Gn[pa * JGP + pb] = n00; Gn[pa * JGP + qb] = n01; Gn[qa * JGP + pb] = n10; Gn[qa * JGP + qb] = n11;
     } else {
-      const T w00 = Wc[(2 * ta) * JGP + pb], w01 = Wc[(2 * ta) * JGP + qb];
-      const T w10 = Wc[(2 * ta + 1) * JGP + pb], w11 = Wc[(2 * ta + 1) * JGP + qb];
-      // W' = W J_b on rows 2ta, 2ta+1
-      Wn[(2 * ta) * JGP + pb] = rot_mix(Rb.c, w00, msb, w01);
-      Wn[(2 * ta) * JGP + qb] = rot_mix(Rb.c, w01, Rb.sp, w00);
-      Wn[(2 * ta + 1) * JGP + pb] = rot_mix(Rb.c, w10, msb, w11);
-      Wn[(2 * ta + 1) * JGP + qb] = rot_mix(Rb.c, w11, Rb.sp, w10);
+      // W' = W J_b on rows 2wa, 2wa+1, columns of pair wb
+      const int r1_ = tid - 256;
+      for (int task = r1_; task < 256; task += 224) {
+        const int wa = task >> 4, wb = task & 15;
+        const int pb = s_rr[step][wb][0], qb = s_rr[step][wb][1];
+        Rot<T> Rb;
+        Rb.c = s_rc[cur][wb]; Rb.sp = s_rsp[cur][wb];
+        const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));
+        const T w00 = Wc[(2 * wa) * JGP + pb], w01 = Wc[(2 * wa) * JGP + qb];
+        const T w10 = Wc[(2 * wa + 1) * JGP + pb], w11 = Wc[(2 * wa + 1) * JGP + qb];
+        Wn[(2 * wa) * JGP + pb] = rot_mix(Rb.c, w00, msb, w01);
+        Wn[(2 * wa) * JGP + qb] = rot_mix(Rb.c, w01, Rb.sp, w00);
+        Wn[(2 * wa + 1) * JGP + pb] = rot_mix(Rb.c, w10, msb, w11);
+        Wn[(2 * wa + 1) * JGP + qb] = rot_mix(Rb.c, w11, Rb.sp, w10);
+      }
     }
     __syncthreads();
   }
+#endif
 #ifndef TNB_EXP_SKIP_EIGEN
   W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
 #endif
@@ -367,17 +482,19 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     chunk_geom(gch, base, ld, c0, len);
     for (int cw = warp * 16; cw < CH; cw += (JT / 32) * 16) {
       if (cw >= len) break;
-      double acc[4][2][CPLX ? 4 : 2];
+      // complex: 3-multiplication form, P1 = wr pr, P2 = wi pi, P3 = (wr + wi)(pr + pi):
+      //   re = P1 - P2,  im = P3 - P1 - P2   (24 DMMAs per k-step instead of 32)
+      double acc[4][2][CPLX ? 6 : 2];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-          for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[mt][nt][r] = 0.0;
+          for (int r = 0; r < (CPLX ? 6 : 2); ++r) acc[mt][nt][r] = 0.0;
 #ifdef TNB_EXP_SKIP_APPLY
       for (int k0 = 0; k0 < 4; k0 += 4) {
 #else
-#pragma unroll 2
+#pragma unroll 1
       for (int k0 = 0; k0 < JP; k0 += 4) {
 #endif
         T av[4], bv[2];
@@ -385,19 +502,26 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JGP + mt * 8 + gq];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) bv[nt] = P[(k0 + tq) * pitch + cw + nt * 8 + gq];
+        if constexpr (CPLX) {
+          double as[4], bs[2];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
+          for (int mt = 0; mt < 4; ++mt) as[mt] = av[mt].x + av[mt].y;
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) {
-            if constexpr (CPLX) {
+          for (int nt = 0; nt < 2; ++nt) bs[nt] = bv[nt].x + bv[nt].y;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
               dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt].x, bv[nt].x);
-              dmma884(acc[mt][nt][2], acc[mt][nt][3], av[mt].x, bv[nt].y);
-              dmma884(acc[mt][nt][0], acc[mt][nt][1], -av[mt].y, bv[nt].y);
-              dmma884(acc[mt][nt][2], acc[mt][nt][3], av[mt].y, bv[nt].x);
-            } else {
-              dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
+              dmma884(acc[mt][nt][2], acc[mt][nt][3], av[mt].y, bv[nt].y);
+              dmma884(acc[mt][nt][4], acc[mt][nt][5], as[mt], bs[nt]);
             }
           }
+        } else {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
         }
       }
       __syncwarp();
@@ -407,8 +531,8 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         for (int nt = 0; nt < 2; ++nt) {
           T* dst = P + (mt * 8 + gq) * pitch + cw + nt * 8 + 2 * tq;
           if constexpr (CPLX) {
-            dst[0] = make_double2(acc[mt][nt][0], acc[mt][nt][2]);
-            dst[1] = make_double2(acc[mt][nt][1], acc[mt][nt][3]);
+            dst[0] = make_double2(acc[mt][nt][0] - acc[mt][nt][2], acc[mt][nt][4] - acc[mt][nt][0] - acc[mt][nt][2]);
+            dst[1] = make_double2(acc[mt][nt][1] - acc[mt][nt][3], acc[mt][nt][5] - acc[mt][nt][1] - acc[mt][nt][3]);
           } else {
             dst[0] = acc[mt][nt][0];
             dst[1] = acc[mt][nt][1];
@@ -435,7 +559,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         const int64_t r = grow(lane);
         if (r >= 0) bulk_s2g(base + r * ld + c0, P + lane * pitch, (uint32_t)(CH * sizeof(T)));
         bulk_commit();
-        bulk_wait_all();  // P may be overwritten (next chunk) or the CTA may exit after this
+        bulk_wait_read();  // P may be overwritten (next chunk) or the CTA may exit after this
       }
     }
   };
@@ -569,13 +693,43 @@ static SvdLayout svd_layout(int dtype, int64_t m, int64_t n) {
   return L;
 }
 
+// How many clusters of `S` CTAs (JT threads, `smem` bytes each) the device can hold at once; cached.
+template <typename T>
+static int max_active_clusters(int S, size_t smem) {
+  static int cache[9][16];  // [S][log2 of the chunk length is implied by smem: index by smem / 16 KB]
+  static bool init = false;
+  if (!init) { for (auto& r : cache) for (int& v : r) v = -1; init = true; }
+  const int slot = (int)(smem >> 14) < 16 ? (int)(smem >> 14) : 15;
+  if (cache[S][slot] >= 0) return cache[S][slot];
+  auto kern = jacobi_round_kernel<T>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(S * 64), 1, 1);
+  cfg.blockDim = dim3(JT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[S][slot] = n;
+  return n;
+}
+
 template <typename T>
 static int launch_round(JacobiArgs& a, int npairs, size_t smem, cudaStream_t st) {
   auto kern = jacobi_round_kernel<T>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  static bool configured = false;
+  if (!configured) {
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(npairs * a.S), 1, 1);
@@ -607,16 +761,31 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, T* Vt, int64_t n, JacobiFlags* 
   a.X = Xt; a.V = Vt; a.n = n; a.L = L; a.ldx = ldx; a.ldv = n; a.nblk = nblk; a.flags = flags;
   a.tol = sqrt((double)(L > 1 ? L : 1)) * 2.220446049250313e-16;
   const int ch_max = cplx ? 256 : 512;
-  int CH = 32;
   const int64_t longest = (L > n || !Vt) ? L : n;
+  auto chunks = [&](int ch) { return (int)((L + ch - 1) / ch) + (Vt ? (int)((n + ch - 1) / ch) : 0); };
+  auto smem_for = [&](int ch) { return ((size_t)JP * (ch + JPAD) + 4 * (size_t)JP * JGP) * sizeof(T); };
+  // CTAs per cluster (<= 8): every pair's cluster must be resident at once (a second wave would double
+  // the round), so candidate sizes are checked against cudaOccupancyMaxActiveClusters -- GPCs differ in
+  // SM count, so this is not simply SMs / size.  The chunk is shortened until there is at least one chunk
+  // per CTA; the size with the fewest chunks per CTA wins, ties go to the smaller cluster (cheaper DSMEM
+  // reduction).
+  int S = 1, CH = 32, best = 1 << 30;
   while (CH < ch_max && CH < longest) CH *= 2;
+  const int ch_top = CH;
+  for (int c = 1; c <= 8; ++c) {
+    int ch = ch_top;
+    while (ch > 32 && chunks(ch) < c) ch /= 2;
+    if (chunks(ch) < c) break;
+    if (c > 1 && max_active_clusters<T>(c, smem_for(ch)) < npairs) continue;
+    const int per = (chunks(ch) + c - 1) / c;
+    const int cost = per * ch;  // elements of a row each CTA walks through
+    if (cost < best) { best = cost; S = c; CH = ch; }
+  }
   a.CH = CH;
   a.nx = (int)((L + CH - 1) / CH);
   a.nv = Vt ? (int)((n + CH - 1) / CH) : 0;
-  int S = 1;
-  while (S * 2 <= 8 && S * 2 <= a.nx + a.nv && npairs * S * 2 <= sm_count()) S *= 2;
   a.S = S;
-  const size_t smem = ((size_t)JP * (CH + JPAD) + 4 * (size_t)JP * JGP) * sizeof(T);
+  const size_t smem = smem_for(CH);
 
   TNB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(JacobiFlags), st));
   static const int fixed_sweeps = getenv("TNB_JACOBI_FIXED_SWEEPS") ? atoi(getenv("TNB_JACOBI_FIXED_SWEEPS")) : 0;
