@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+{
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+for v in EIGEN ALL; do
+  TNB_LIB_PATH=$PWD/scratch/exp/libtnb_SKIP_$v.so TNB_JACOBI_FIXED_SWEEPS=5 timeout 120 python scratch/jac_phases.py
+done
+TNB_JACOBI_FIXED_SWEEPS=5 timeout 120 python scratch/jac_phases.py
+timeout 300 python scratch/site_ops.py svd 3
+} > gpurun_out/exp4.log 2>&1
+tail -40 gpurun_out/exp4.log

@@ -205,6 +205,55 @@ def test_qr(cplx):
     assert np.all(np.isfinite(np.asarray(q))) and rel(np.asarray(q) @ np.asarray(r), a) < TOL
 
 
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_qr_many_columns(cplx):
+    """k >= 128 takes the Gram-Schmidt (BCGS2 + CholeskyQR) path of qr.cu; numerically dependent or very
+    ill-conditioned inputs must trip its device checks and come out of the Householder path just as good."""
+    torch, _lib, dv = _mods()
+    rng = np.random.default_rng(14)
+
+    def check(a, tol=TOL):
+        m, n = a.shape
+        k = min(m, n)
+        q, r = dv.qr(dv.DevArray.from_host(a))
+        q, r = np.asarray(q), np.asarray(r)
+        assert q.shape == (m, k) and r.shape == (k, n)
+        assert np.all(np.isfinite(q)) and np.all(np.isfinite(r))
+        assert rel(q @ r, a) < tol, (m, n)
+        assert np.linalg.norm(q.conj().T @ q - np.eye(k)) < 1e-12 * k, (m, n)
+        assert np.array_equal(np.tril(r, -1), np.zeros_like(r)), (m, n)
+        return q, r
+
+    for m, n in [(300, 200), (200, 300), (1000, 130), (129, 129), (640, 192)]:
+        a = rnd(rng, (m, n), cplx)
+        q, r = check(a)
+        rr = np.linalg.qr(a, mode="r")
+        k = min(m, n)
+        assert rel(np.abs(np.diag(r)), np.abs(np.diag(rr))[:k]) < 1e-11, (m, n)
+    for scale in (1e170, 1e-170):
+        a = rnd(rng, (300, 200), cplx)
+        q, r = dv.qr(dv.DevArray.from_host(a * scale))
+        assert rel(np.asarray(q) @ (np.asarray(r) / scale), a) < TOL
+    # dependent and zero columns
+    a = rnd(rng, (400, 256), cplx)
+    a[:, 70] = 0
+    a[:, 150] = a[:, 20]
+    a[:, 200] = a[:, 3] - 2 * a[:, 130]
+    check(a)
+    # columns graded over 12 decades: column-wise backward error
+    a = rnd(rng, (400, 200), cplx) * np.logspace(0, -12, 200)[None, :]
+    q, r = check(a)
+    err = np.linalg.norm(q @ r - a, axis=0) / np.linalg.norm(a, axis=0)
+    assert err.max() < 1e-11
+    # condition number 1e12 (singular values graded, not the columns)
+    u, _ = np.linalg.qr(rnd(rng, (300, 160), cplx))
+    v, _ = np.linalg.qr(rnd(rng, (160, 160), cplx))
+    a = (u * np.logspace(0, -12, 160)[None, :]) @ v.conj().T
+    check(a)
+
+
 SVD_SHAPES = [(1, 1), (1, 6), (6, 1), (2, 2), (12, 20), (20, 12), (16, 16), (17, 17), (33, 31), (64, 128), (128, 64),
               (100, 100), (256, 128), (300, 520), (512, 512)]
 

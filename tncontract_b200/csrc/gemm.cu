@@ -354,18 +354,25 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
   const bool a_kc = (opA == TNB_OP_N || opA == TNB_OP_J);
   // op N on B: stored K x N (n contiguous). op T/C: stored N x K (k contiguous).
   const bool b_kc = !(opB == TNB_OP_N || opB == TNB_OP_J);
-  // skinny problems: smaller tiles waste fewer DMMAs and fill more SMs
+  // skinny problems: smaller tiles waste fewer DMMAs and fill more SMs -- unless split-K can fill the
+  // machine with full-size tiles (8 warps per CTA, twice the operand reuse), which is then preferred
   const int64_t big_tiles = cplx ? ((M + 127) / 128) * ((N + 63) / 64) : ((M + 127) / 128) * ((N + 127) / 128);
-  const bool small = (M <= 64) || (N <= (cplx ? 32 : 64)) || (big_tiles * batch < (int64_t)sm_count());
+  bool small = (M <= 64) || (N <= (cplx ? 32 : 64)) || (big_tiles * batch < (int64_t)sm_count());
   if (splitk_ws && batch == 1) {
-    const int64_t bm = small ? 64 : 128, bn = cplx ? (small ? 32 : 64) : (small ? 64 : 128), bk = cplx ? 8 : 16;
-    const int64_t tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
-    int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;  // aim at ~2 CTAs per SM
-    const int64_t max_by_k = K / (bk * 16);                       // keep >= 16 k-steps per split
+    const int64_t bk = cplx ? 8 : 16;
+    const int64_t max_by_k = K / (bk * 16);  // keep >= 16 k-steps per split
     const int64_t max_by_ws = (int64_t)(splitk_bytes / ((size_t)M * N * (cplx ? 16 : 8)));
-    if (want > max_by_k) want = max_by_k;
-    if (want > max_by_ws) want = max_by_ws;
-    if (want > 64) want = 64;
+    auto plan = [&](int64_t tiles) {
+      int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;  // aim at ~2 CTAs per SM
+      if (want > max_by_k) want = max_by_k;
+      if (want > max_by_ws) want = max_by_ws;
+      if (want > 64) want = 64;
+      return want < 1 ? (int64_t)1 : want;
+    };
+    if (small && M > 64 && N > (cplx ? 32 : 64) && big_tiles * plan(big_tiles) * 5 >= (int64_t)sm_count() * 4) small = false;
+    const int64_t bm = small ? 64 : 128, bn = cplx ? (small ? 32 : 64) : (small ? 64 : 128);
+    const int64_t tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
+    const int64_t want = plan(tiles);
     if (want >= 2) {
       int64_t kps = (K + want - 1) / want;
       kps = ((kps + bk - 1) / bk) * bk;

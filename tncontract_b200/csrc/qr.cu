@@ -763,8 +763,10 @@ constexpr int QR_NBO = 128;  // outer block: trailing updates and the explicit Q
 
 struct QrLayout {
   int64_t k, ldw, ldv, nouter;
-  size_t off_w, off_v, off_t, off_w1, off_w2, off_sc, off_sk, sk_bytes, total;
+  size_t off_w, off_v, off_t, off_w1, off_w2, off_sc, off_sk, sk_bytes, off_p2, off_cb, off_bc, total;
 };
+
+constexpr int QR_CB = 64;  // column block of the Gram-Schmidt path (qr_bcgs2)
 
 static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
   QrLayout L;
@@ -784,6 +786,9 @@ static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
   // split-K scratch for the (jb x n2 x m) products: up to 16 partials of a 128 x wide block
   L.sk_bytes = (m >= 1024) ? align_up((size_t)16 * QR_NBO * wide * es) : 0;
   L.off_sk = o; o += L.sk_bytes;
+  L.off_p2 = o; o += align_up((size_t)m * QR_CB * es);    // qr_bcgs2: second panel buffer
+  L.off_cb = o; o += align_up((size_t)L.k * QR_CB * es);  // qr_bcgs2: [Q^H W; W^H W] of pass 2
+  L.off_bc = o; o += align_up((size_t)L.k * QR_CB * es);  // qr_bcgs2: [-C R^-1; R^-1] of the current pass
   L.total = o;
   return L;
 }
@@ -833,6 +838,237 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
   TNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
   ++g_launches;
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Block classical Gram-Schmidt with reorthogonalisation and Pythagorean inner products (BCGS-PIP+, Carson,
+// Lund, Rozloznik, Thomas 2021) -- the QR path for matrices with many columns.  Every O(m n^2) operation
+// is a DMMA GEMM over all SMs; the only small serial kernel is the 64 x 64 Cholesky factor + triangular
+// inverse below (two per column block).  With Qj = Q[:, :j] and W = A[:, J] stored next to it as Q[:, J],
+// one pass over a block J of QR_CB columns is two large GEMMs:
+//     [C; G0] = [Qj, W]^H W              (K = m, split-K)
+//     G  = G0 - C^H C = (W - Qj C)^H (W - Qj C) = R^H R            (Pythagoras; 64 x 64 kernel)
+//     W <- (W - Qj C) R^-1 = [Qj, W] [-C R^-1; R^-1]               (K = j + 64)
+// and two passes give  Q[:, J] = W,  R[J, J] = R2 R1,  R[:j, J] = C1 + C2 R1.
+// A first-pass Cholesky pivot below 1e-10 of its diagonal entry, or a second-pass Gram matrix that is not
+// close to I (pivot < 1/4: the first pass lost orthogonality -- cancellation in the Pythagorean step,
+// numerically dependent columns), raises a device flag; the caller then runs the Householder path on the
+// untouched A.
+// ---------------------------------------------------------------------------------------------------
+constexpr int CI_N = QR_CB;       // matrix order handled by chol_inv_kernel
+constexpr int CI_P = CI_N + 1;    // shared-memory pitch
+constexpr int CI_THREADS = 512;
+
+// G (n x n Hermitian, n <= 64; upper triangle read) -> R (upper, G = R^H R, real positive diagonal) and
+// Rinv = R^-1 (upper); strictly lower triangles are written as zeros.  One CTA.  flag[0] is set when a pivot
+// is <= rel_floor * (its original diagonal entry) or <= abs_floor.
+template <typename T>
+__global__ void __launch_bounds__(CI_THREADS) chol_inv_kernel(const T* G, int64_t ldg, int n, T* R, int64_t ldr,
+                                                              T* Rinv, int64_t ldri, double rel_floor,
+                                                              double abs_floor, int* flag) {
+  typedef Num<T> N_;
+  extern __shared__ __align__(16) unsigned char ci_smem[];
+  T* A = reinterpret_cast<T*>(ci_smem);  // [CI_N][CI_P]  G -> R
+  T* X = A + CI_N * CI_P;                // [CI_N][CI_P]  R^-1
+  T* Y = X + CI_N * CI_P;                // [CI_N][CI_P]  scratch of the inversion
+  __shared__ double diag0[CI_N];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  for (int idx = tid; idx < CI_N * CI_N; idx += CI_THREADS) {
+    const int i = idx / CI_N, j = idx - i * CI_N;
+    T v = N_::zero();
+    if (i < n && j < n) { if (j >= i) v = G[(int64_t)i * ldg + j]; }
+    else if (i == j) v = N_::one();  // identity padding
+    A[i * CI_P + j] = v;
+  }
+  __syncthreads();
+  if (tid < CI_N) diag0[tid] = N_::real(A[tid * CI_P + tid]);
+  // right-looking Cholesky on the upper triangle, rows kept unscaled (Schur complements); thread owns
+  // column k and rows i0 .. i0 + 7
+  const int k = tid & (CI_N - 1), i0 = (tid / CI_N) * (CI_N * CI_N / CI_THREADS);
+  constexpr int RPT = CI_N * CI_N / CI_THREADS;  // rows per thread (8)
+  bool bad = false;
+  for (int j = 0; j < CI_N; ++j) {
+    __syncthreads();
+    const double piv = N_::real(A[j * CI_P + j]);
+    if (!(piv > rel_floor * diag0[j]) || !(piv > abs_floor)) bad = true;
+    if (i0 + RPT - 1 > j && k > j) {
+      const double ipiv = __drcp_rn(piv);
+      const T rjk = A[j * CI_P + k];
+#pragma unroll
+      for (int ii = 0; ii < RPT; ++ii) {
+        const int i = i0 + ii;
+        if (i > j && k >= i) {
+          const T f = N_::scale(N_::conj(A[j * CI_P + i]), ipiv);
+          A[i * CI_P + k] = N_::sub(A[i * CI_P + k], N_::mul(f, rjk));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (bad && tid == 0) s_bad = 1;
+  double rs[RPT];
+#pragma unroll
+  for (int ii = 0; ii < RPT; ++ii) rs[ii] = rsqrt(N_::real(A[(i0 + ii) * CI_P + i0 + ii]));
+  __syncthreads();
+#pragma unroll
+  for (int ii = 0; ii < RPT; ++ii) {
+    const int i = i0 + ii;
+    T v = (k >= i) ? N_::scale(A[i * CI_P + k], rs[ii]) : N_::zero();
+    if (k == i) v = N_::from(N_::real(v), 0.0);
+    A[i * CI_P + k] = v;
+    // inverse of the diagonal: 1 / R[i][i] = rs * (1 / (d rs^2)) ... R[i][i] = d * rs with d the pivot: 1/R = 1/(d rs)
+    X[i * CI_P + k] = (k == i) ? N_::from(1.0 / N_::real(v), 0.0) : N_::zero();
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) flag[0] = 1;
+    // still write finite output (identity) so that the queued GEMMs of the caller stay harmless
+    for (int idx = tid; idx < n * n; idx += CI_THREADS) {
+      const int i = idx / n, j = idx - i * n;
+      R[(int64_t)i * ldr + j] = (i == j) ? N_::one() : N_::zero();
+      Rinv[(int64_t)i * ldri + j] = (i == j) ? N_::one() : N_::zero();
+    }
+    return;
+  }
+  // X = A^-1 by recursive doubling over diagonal blocks of size b = 1, 2, .. 32:
+  //   X12 = -X11 (A12 X22) for every pair of adjacent diagonal blocks
+  for (int b = 1; b < CI_N; b *= 2) {
+    const int nent = CI_N * b / 2;
+    for (int e = tid; e < nent; e += CI_THREADS) {
+      const int blk = e / (b * b), r = (e / b) % b, c = e % b;
+      const int s0 = blk * 2 * b;
+      T sum = N_::zero();
+      for (int q = 0; q <= c; ++q) sum = N_::fma(A[(s0 + r) * CI_P + s0 + b + q], X[(s0 + b + q) * CI_P + s0 + b + c], sum);
+      Y[(s0 + r) * CI_P + s0 + b + c] = sum;
+    }
+    __syncthreads();
+    for (int e = tid; e < nent; e += CI_THREADS) {
+      const int blk = e / (b * b), r = (e / b) % b, c = e % b;
+      const int s0 = blk * 2 * b;
+      T sum = N_::zero();
+      for (int q = r; q < b; ++q) sum = N_::fma(X[(s0 + r) * CI_P + s0 + q], Y[(s0 + q) * CI_P + s0 + b + c], sum);
+      X[(s0 + r) * CI_P + s0 + b + c] = N_::sub(N_::zero(), sum);
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < n * n; idx += CI_THREADS) {
+    const int i = idx / n, j = idx - i * n;
+    R[(int64_t)i * ldr + j] = A[i * CI_P + j];
+    Rinv[(int64_t)i * ldri + j] = X[i * CI_P + j];
+  }
+}
+
+template <typename T>
+__global__ void scale_by_kernel(T* x, int64_t n, const double* s) {
+  const double f = s[0];
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) x[i] = Num<T>::scale(x[i], f);
+}
+
+// returns 0 on success, 1 when the device flag asks for the Householder path, < 0 on errors
+template <typename T>
+static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws,
+                    int scale_mode, double** scale_out, cudaStream_t st) {
+  typedef Num<T> N_;
+  const QrLayout L = qr_layout(dtype, m, n);
+  char* base = (char*)ws;
+  const int64_t k = L.k;
+  T* Wsc = (T*)(base + L.off_w);                      // scaled copy of the columns beyond k (wide matrices)
+  T* Qb = Q ? (T*)Q : (T*)(base + L.off_v);           // m x k orthonormal factor
+  const int64_t ldq = Q ? k : L.ldv;
+  T* P2 = (T*)(base + L.off_p2);                      // m x QR_CB
+  T* Sb = (T*)(base + L.off_cb);                      // k x QR_CB   [C2; G0] of pass 2
+  T* Bc = (T*)(base + L.off_bc);                      // k x QR_CB   [-C R^-1; R^-1]
+  T* R1 = (T*)(base + L.off_t);                       // two QR_CB x QR_CB matrices
+  T* R2 = R1 + QR_CB * QR_CB;
+  T* Rg = (T*)R;
+  void* sk = L.sk_bytes ? (void*)(base + L.off_sk) : nullptr;
+  int* flag = (int*)(base + L.off_sc + 128);
+  double* sc = nullptr;
+  if (scale_mode != 0) {
+    unsigned long long* bits = (unsigned long long*)(base + L.off_sc);
+    sc = (double*)(base + L.off_sc) + 1;
+    TNB_CUDA_CHECK(cudaMemsetAsync(bits, 0, sizeof(unsigned long long), st));
+    amax_kernel<T><<<blocks_for(m * n), 256, 0, st>>>((const T*)A, lda, m, n, bits);
+    TNB_LAUNCH_CHECK();
+    pow2_scale_kernel<<<1, 1, 0, st>>>(bits, sc);
+    TNB_LAUNCH_CHECK();
+    if (scale_out) *scale_out = sc;
+  }
+  TNB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  TNB_CUDA_CHECK(cudaMemsetAsync(Rg, 0, (size_t)k * n * sizeof(T), st));
+  auto kern = chol_inv_kernel<T>;
+  constexpr size_t ci_smem = (size_t)3 * CI_N * CI_P * sizeof(T);
+  static bool configured = false;
+  if (!configured) {
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ci_smem));
+    configured = true;
+  }
+  auto chol_inv = [&](const T* G, int64_t ldg, T* Rout, T* Rinv, double rel_floor, double abs_floor, int bj) -> int {
+    ProfScope prof(KC_QR_PANEL, st, (sizeof(T) == 16 ? 4.0 : 1.0) * 2.0 / 3.0 * (double)bj * bj * bj);
+    kern<<<1, CI_THREADS, ci_smem, st>>>(G, ldg, bj, Rout, QR_CB, Rinv, QR_CB, rel_floor, abs_floor, flag);
+    TNB_LAUNCH_CHECK();
+    ++g_launches;
+    return 0;
+  };
+  int rc;
+  // one pass: S (ld lds) <- [Qj, W]^H W;  G in place;  Rout, Bc;  P2 <- [Qj, W] Bc;  W <- P2
+  auto pass = [&](int64_t j0, int64_t bj, T* Qp, T* S, int64_t lds, T* Rout, double rel_floor, double abs_floor) -> int {
+    const int64_t kk = j0 + bj;
+    int r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, kk, bj, m, 1, 0, Qb, ldq, 0, Qp, ldq, 0, 0, 0, S, lds, 0, 1, sk, L.sk_bytes, st);
+    if (r_) return r_;
+    T* G = S + j0 * lds;
+    T* Ri = Bc + j0 * QR_CB;
+    if (j0 > 0) {
+      r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, bj, bj, j0, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, L.sk_bytes, st);
+      if (r_) return r_;
+    }
+    chol_inv(G, lds, Rout, Ri, rel_floor, abs_floor, (int)bj);
+    if (j0 > 0) {
+      r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, bj, bj, -1, 0, S, lds, 0, Ri, QR_CB, 0, 0, 0, Bc, QR_CB, 0, 1, st);
+      if (r_) return r_;
+    }
+    r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, bj, kk, 1, 0, Qb, ldq, 0, Bc, QR_CB, 0, 0, 0, P2, QR_CB, 0, 1, sk, L.sk_bytes, st);
+    if (r_) return r_;
+    copy2d_kernel<T><<<blocks_for(m * bj), 256, 0, st>>>(P2, QR_CB, Qp, ldq, m, bj, nullptr);
+    TNB_LAUNCH_CHECK();
+    return 0;
+  };
+  for (int64_t j0 = 0; j0 < k; j0 += QR_CB) {
+    const int64_t bj = (k - j0 < QR_CB) ? (k - j0) : QR_CB;
+    T* Qp = Qb + j0;
+    T* Rj = Rg + j0;                // R[0:j0, J], ld n  (pass 1 leaves C1 there, and G0 -> G in R[J, J])
+    T* Rjj = Rg + j0 * n + j0;
+    copy2d_kernel<T><<<blocks_for(m * bj), 256, 0, st>>>((const T*)A + j0, lda, Qp, ldq, m, bj, sc);
+    TNB_LAUNCH_CHECK();
+    rc = pass(j0, bj, Qp, Rj, n, R1, 1e-10, 0.0);
+    if (rc) return rc;
+    rc = pass(j0, bj, Qp, Sb, QR_CB, R2, 0.0, 0.25);
+    if (rc) return rc;
+    if (j0 > 0) {  // R[:j0, J] = C1 + C2 R1
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, bj, bj, 1, 0, Sb, QR_CB, 0, R1, QR_CB, 0, 1, 0, Rj, n, 0, 1, st);
+      if (rc) return rc;
+    }
+    rc = gemm(dtype, TNB_OP_N, TNB_OP_N, bj, bj, bj, 1, 0, R2, QR_CB, 0, R1, QR_CB, 0, 0, 0, Rjj, n, 0, 1, st);
+    if (rc) return rc;
+  }
+  if (n > k) {  // wide: R[:, k:] = Q^H (scale * A[:, k:])
+    copy2d_kernel<T><<<blocks_for(m * (n - k)), 256, 0, st>>>((const T*)A + k, lda, Wsc, L.ldw, m, n - k, sc);
+    TNB_LAUNCH_CHECK();
+    rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, k, n - k, m, 1, 0, Qb, ldq, 0, Wsc, L.ldw, 0, 0, 0, Rg + k, n, 0, 1, sk, L.sk_bytes, st);
+    if (rc) return rc;
+  }
+  if (scale_mode == 1) {
+    scale_by_kernel<T><<<blocks_for(k * n), 256, 0, st>>>(Rg, k * n, sc + 1);
+    TNB_LAUNCH_CHECK();
+  }
+  int h = 0;
+  TNB_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA_CHECK(cudaStreamSynchronize(st));
+  (void)sizeof(N_);
+  return h ? 1 : 0;
 }
 
 // scale_mode 0: factor A as it is; 1: factor 2^e A (e from max|A|, so no dot product can overflow) and
@@ -952,8 +1188,18 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
 }
 
 // internal entry used by svd.cu as well
+// kernel experiments: TNB_QR_BCGS=0 forces the Householder path everywhere
+static const int g_qr_bcgs = getenv("TNB_QR_BCGS") ? atoi(getenv("TNB_QR_BCGS")) : 1;
+
 int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, int scale_mode,
        double** scale_out, cudaStream_t st) {
+  // many columns: Gram-Schmidt path (all GEMMs); falls back to Householder when its device checks trip
+  const int64_t k = m < n ? m : n;
+  if (g_qr_bcgs && R && k >= 2 * QR_CB) {
+    const int rc = (dtype == TNB_F64) ? qr_bcgs2<double>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st)
+                                      : qr_bcgs2<cplx>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st);
+    if (rc <= 0) return rc;
+  }
   if (dtype == TNB_F64) return qr_impl<double>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st);
   return qr_impl<cplx>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st);
 }
