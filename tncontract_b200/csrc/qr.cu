@@ -893,17 +893,12 @@ __global__ void __launch_bounds__(CI_THREADS) chol_inv_kernel(const T* G, int64_
     __syncthreads();
     const double piv = N_::real(A[j * CI_P + j]);
     if (!(piv > rel_floor * diag0[j]) || !(piv > abs_floor)) bad = true;
-    if (i0 + RPT - 1 > j && k > j) {
+    // rows of this thread inside the active triangle: j < i <= k (whole warps drop out as j advances)
+    const int ilo = (i0 > j + 1) ? i0 : j + 1, ihi = (i0 + RPT - 1 < k) ? i0 + RPT - 1 : k;
+    if (ilo <= ihi) {
       const double ipiv = __drcp_rn(piv);
-      const T rjk = A[j * CI_P + k];
-#pragma unroll
-      for (int ii = 0; ii < RPT; ++ii) {
-        const int i = i0 + ii;
-        if (i > j && k >= i) {
-          const T f = N_::scale(N_::conj(A[j * CI_P + i]), ipiv);
-          A[i * CI_P + k] = N_::sub(A[i * CI_P + k], N_::mul(f, rjk));
-        }
-      }
+      const T rjk = N_::scale(A[j * CI_P + k], ipiv);
+      for (int i = ilo; i <= ihi; ++i) A[i * CI_P + k] = N_::sub(A[i * CI_P + k], N_::mul(N_::conj(A[j * CI_P + i]), rjk));
     }
   }
   __syncthreads();

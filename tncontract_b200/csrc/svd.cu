@@ -119,7 +119,7 @@ template <typename T> struct Rot { double c; T sp; };
 //   c^2 = (1 + |tau| rh)/2,  sp = g sign(tau) rh / (2 c)       (|theta| <= pi/4, the inner rotation)
 // -- two rsqrt, no division, no square root (X has unit Frobenius norm: nothing overflows).
 // The pair counts as converged when |g|^2 <= tol2 alpha beta; bit 0 of `state` records a rotation,
-// bit 1 one whose squared cosine exceeded 1e-20 (see jacobi_finish_sweep_kernel).
+// bit 1 one whose squared cosine exceeded 1e-14 (see jacobi_finish_sweep_kernel).
 template <typename T>
 __device__ __forceinline__ Rot<T> make_rot_vals(double alpha, double beta, T gam, double tol2, unsigned& state) {
   typedef Num<T> N_;
@@ -128,7 +128,7 @@ __device__ __forceinline__ Rot<T> make_rot_vals(double alpha, double beta, T gam
   const double ag2 = N_::abs2(gam);
   const double ab = alpha * beta;
   if (ab > 0.0 && ag2 > tol2 * ab) {
-    state |= (ag2 > 1e-20 * ab) ? 3u : 1u;
+    state |= (ag2 > 1e-14 * ab) ? 3u : 1u;
     const double tau = 0.5 * (beta - alpha);
     const double rh = rsqrt(fma(tau, tau, ag2));
     const double c2 = fma(0.5 * fabs(tau), rh, 0.5);
@@ -574,8 +574,9 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
 }
 
 // Closes a sweep.  state bit 0: some pair was rotated (cosine above tol); bit 1: some rotated pair had a
-// squared cosine above 1e-20.  Cyclic Jacobi converges quadratically, so a sweep whose largest cosine was
-// already below 1e-10 leaves every cosine far below tol: the confirming sweep is skipped.
+// squared cosine above 1e-14.  Cyclic Jacobi converges quadratically (the largest cosine of a sweep is about
+// the square of the previous sweep's), so a sweep whose largest cosine was already below 1e-7 leaves
+// every cosine at the level of tol: the confirming sweep is skipped.
 __global__ void jacobi_finish_sweep_kernel(JacobiFlags* f, int fixed) {
   if (f->converged) return;
   f->sweeps += 1;
