@@ -6,9 +6,10 @@
 // mma.sync.m8n8k4.f64 (one DMMA.8x8x4 per instruction).  Layout of one CTA:
 //   * real:    128x128 C tile, 8 warps (2 x 4), warp tile 64x32, BK = 16
 //   * complex: 128x64  C tile, 8 warps (4 x 2), warp tile 32x32, BK = 8,
-//              4 DMMAs per (m8,n8,k4) tile pair: re += ar*br, re += (-ai)*bi,
-//              im += ar*bi, im += ai*br (interleaved re/im stays interleaved in
-//              shared memory; fragments are 16-byte LDS)
+//              3 DMMAs per (m8,n8,k4) tile pair (3-multiplication form):
+//              P1 += ar*br, P2 += ai*bi, P3 += (ar+ai)*(br+bi); re = P1 - P2,
+//              im = P3 - P1 - P2 in the epilogue (interleaved re/im stays
+//              interleaved in shared memory; fragments are 16-byte LDS)
 //   * a "small" variant (64x64 real / 64x32 complex, 4 warps) for skinny shapes
 // Operands are staged by a 4-stage cp.async (LDGSTS, 16-byte, zero-fill at the
 // edges) pipeline.  Either operand may be K-contiguous ([mn][k]) or
@@ -125,13 +126,15 @@ gemm_kernel(GemmArgs g) {
     ldc = g.N;
   }
 
-  double acc[MT][NT][CPLX ? 4 : 2];
+  // complex: 3-multiplication form, three accumulator pairs per 8x8 tile:
+  //   P1 = ar br, P2 = ai bi, P3 = (ar + ai)(br + bi);  re = P1 - P2, im = P3 - P1 - P2
+  double acc[MT][NT][CPLX ? 6 : 2];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < NT; ++j)
 #pragma unroll
-      for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[i][j][r] = 0.0;
+      for (int r = 0; r < (CPLX ? 6 : 2); ++r) acc[i][j][r] = 0.0;
 
   const int KT = (int)((kend - kbeg + BK - 1) / BK);
 
@@ -174,19 +177,18 @@ gemm_kernel(GemmArgs g) {
 #pragma unroll
           for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       } else {
-        double nai[MT];
+        double as_[MT], bs_[NT];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) { af[i].y *= sgnA; nai[i] = -af[i].y; }
+        for (int i = 0; i < MT; ++i) { af[i].y *= sgnA; as_[i] = af[i].x + af[i].y; }
 #pragma unroll
-        for (int j = 0; j < NT; ++j) bf[j].y *= sgnB;
+        for (int j = 0; j < NT; ++j) { bf[j].y *= sgnB; bs_[j] = bf[j].x + bf[j].y; }
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
-            dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);  // re += ar*br
-            dmma884(acc[i][j][2], acc[i][j][3], af[i].x, bf[j].y);  // im += ar*bi
-            dmma884(acc[i][j][0], acc[i][j][1], nai[i], bf[j].y);   // re -= ai*bi
-            dmma884(acc[i][j][2], acc[i][j][3], af[i].y, bf[j].x);  // im += ai*br
+            dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);  // P1 += ar*br
+            dmma884(acc[i][j][2], acc[i][j][3], af[i].y, bf[j].y);  // P2 += ai*bi
+            dmma884(acc[i][j][4], acc[i][j][5], as_[i], bs_[j]);    // P3 += (ar+ai)*(br+bi)
           }
       }
     }
@@ -219,8 +221,8 @@ gemm_kernel(GemmArgs g) {
         }
       } else {
         const double2 al = make_double2(alpha_r, alpha_i), be = make_double2(g.beta_r, g.beta_i);
-        double2 v0 = cmul(al, make_double2(acc[i][j][0], acc[i][j][2]));
-        double2 v1 = cmul(al, make_double2(acc[i][j][1], acc[i][j][3]));
+        double2 v0 = cmul(al, make_double2(acc[i][j][0] - acc[i][j][2], acc[i][j][4] - acc[i][j][0] - acc[i][j][2]));
+        double2 v1 = cmul(al, make_double2(acc[i][j][1] - acc[i][j][3], acc[i][j][5] - acc[i][j][1] - acc[i][j][3]));
         if (has_beta) {
           v0 = cadd(v0, cmul(be, dst[0]));
           if (col + 1 < g.N) v1 = cadd(v1, cmul(be, dst[1]));

@@ -63,6 +63,13 @@ constexpr int JT = 512;      // threads per CTA: 2 x (JP/2)^2 -- G blocks on the
 constexpr int JGP = JP + 4;  // pitch of the small matrices in shared memory (= 4 mod 8: conflict-free DMMA fragments)
 constexpr int JPAD = 4;      // panel pitch = CH + JPAD for the same reason
 constexpr int MAX_SWEEPS = 60;
+
+#ifdef TNB_EXP_STAMPS
+__device__ long long g_jac_dbg[128];  // kernel experiments: clock64 stamps of the rotation phase (CTA 0)
+#define JSTAMP(k, cond) do { if (blockIdx.x == 0 && (cond)) g_jac_dbg[k] = clock64(); } while (0)
+#else
+#define JSTAMP(k, cond) do { } while (0)
+#endif
 constexpr int GRAM_TILES = 10;  // upper 8 x 8 tiles of the 4 x 4 tile grid of a JP x JP Hermitian matrix
 constexpr int GRAM_UPW = 5;     // Gram work units (tile, eighth of a chunk) per warp: 10 * 8 / 16
 
@@ -401,8 +408,10 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     s_rsp[0][lane] = r.sp;
   }
   __syncthreads();
+  JSTAMP(0, tid == 0);
   for (int step = 0; step < nsteps; ++step) {
     const int cur = step & 1;
+    JSTAMP(1 + 4 * step, tid == ROTW * 32);
     const T* Gc = G + cur * (JP * JGP);
     T* Gn = G + (cur ^ 1) * (JP * JGP);
     const T* Wc = W + cur * (JP * JGP);
@@ -423,6 +432,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         s_rc[cur ^ 1][lane] = r.c;
         s_rsp[cur ^ 1][lane] = r.sp;
       }
+      JSTAMP(2 + 4 * step, lane == 0);
     } else if (warp < 8) {
       const int pa = s_rr[step][ta][0], qa = s_rr[step][ta][1];
       const int pb = s_rr[step][tb][0], qb = s_rr[step][tb][1];
@@ -445,6 +455,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         if (Ra.c != 1.0 || N_::abs2(Ra.sp) != 0.0) { n01 = N_::zero(); n10 = N_::zero(); }
       }
       Gn[pa * JGP + pb] = n00; Gn[pa * JGP + qb] = n01; Gn[qa * JGP + pb] = n10; Gn[qa * JGP + qb] = n11;
+      JSTAMP(3 + 4 * step, tid == 0);
     } else {
       // W' = W J_b on rows 2wa, 2wa+1, columns of pair wb
       const int r1_ = tid - 256;
@@ -461,9 +472,11 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         Wn[(2 * wa + 1) * JGP + pb] = rot_mix(Rb.c, w10, msb, w11);
         Wn[(2 * wa + 1) * JGP + qb] = rot_mix(Rb.c, w11, Rb.sp, w10);
       }
+      JSTAMP(4 + 4 * step, tid == 256);
     }
     __syncthreads();
   }
+  JSTAMP(1 + 4 * nsteps, tid == 0);
 #endif
 #ifndef TNB_EXP_SKIP_EIGEN
   W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
@@ -932,6 +945,14 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
 }
 
 }  // namespace tnb
+
+#ifdef TNB_EXP_STAMPS
+extern "C" int tnb_debug_jacobi_stamps(long long* out, int n) {
+  if (!out || n <= 0 || n > 128) return TNB_E_ARG;
+  TNB_CUDA_CHECK(cudaMemcpyFromSymbol(out, tnb::g_jac_dbg, (size_t)n * sizeof(long long)));
+  return 0;
+}
+#endif
 
 extern "C" size_t tnb_svd_workspace(int dtype, int64_t m, int64_t n) {
   if (m <= 0 || n <= 0 || (dtype != TNB_F64 && dtype != TNB_C128)) return 0;
