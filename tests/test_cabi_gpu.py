@@ -254,6 +254,28 @@ def test_qr_many_columns(cplx):
     check(a)
 
 
+
+@pytest.mark.gpu
+def test_get_into_host_buffer():
+    """DevArray.get(out=...) copies into a caller-provided (pinned) host buffer, also from strided views."""
+    torch, _lib, dv = _mods()
+    rng = np.random.default_rng(15)
+    a = rnd(rng, (6, 5, 4), True)
+    d = dv.DevArray.from_host(a)
+    buf = torch.empty((6, 5, 4), dtype=torch.complex128).pin_memory()
+    assert d.get(out=buf) is buf
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.numpy(), a)
+    v = d.transpose((2, 0, 1)) if hasattr(d, "transpose") else None
+    if v is not None:
+        out = np.empty((4, 6, 5), dtype=np.complex128)
+        v.get(out=out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out, a.transpose(2, 0, 1))
+    with pytest.raises(ValueError):
+        d.get(out=np.empty((5, 6, 4), dtype=np.complex128))
+
+
 SVD_SHAPES = [(1, 1), (1, 6), (6, 1), (2, 2), (12, 20), (20, 12), (16, 16), (17, 17), (33, 31), (64, 128), (128, 64),
               (100, 100), (256, 128), (300, 520), (512, 512)]
 

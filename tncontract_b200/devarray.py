@@ -91,8 +91,19 @@ class DevArray:
             out = out.astype(dtype)
         return out
 
-    def get(self):
-        return self.__array__()
+    def get(self, out=None):
+        """Host copy.  With ``out`` (a torch CPU tensor -- pinned for full PCIe speed -- or a NumPy array of the
+        same shape and dtype) the copy is enqueued on the current stream into that buffer and ``out`` is
+        returned; the caller synchronises (``torch.cuda.synchronize()``) before reading it."""
+        if out is None:
+            return self.__array__()
+        src = self if self.t.is_contiguous() else self.copy()
+        dst = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
+        if tuple(dst.shape) != tuple(src.t.shape) or dst.dtype != src.t.dtype:
+            raise ValueError("get(out=...): shape/dtype mismatch %s %s vs %s %s" %
+                             (tuple(dst.shape), dst.dtype, tuple(src.t.shape), src.t.dtype))
+        dst.copy_(src.t, non_blocking=True)
+        return out
 
     def item(self):
         return self.__array__().item()
