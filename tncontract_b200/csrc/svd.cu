@@ -60,7 +60,8 @@ int permute_view(int dtype, const void* in, int rank, const int64_t* oshape, con
 constexpr int JB = 16;       // Jacobi block width (columns)
 constexpr int JP = 2 * JB;   // columns in a block pair
 constexpr int JT = 512;      // threads per CTA: 2 x (JP/2)^2 -- G blocks on the first half, W blocks on the second
-constexpr int JGP = JP + 4;  // pitch of the small matrices in shared memory (= 4 mod 8: conflict-free DMMA fragments)
+constexpr int JGP = JP + 4;  // pitch of W / Gram partials in shared memory (= 4 mod 8: conflict-free DMMA fragments)
+constexpr int JGG = JP + 1;  // pitch of G (rotation phase only): row AND column accesses are conflict-free
 constexpr int JPAD = 4;      // panel pitch = CH + JPAD for the same reason
 constexpr int MAX_SWEEPS = 60;
 
@@ -148,7 +149,7 @@ __device__ __forceinline__ Rot<T> make_rot_vals(double alpha, double beta, T gam
 template <typename T>
 __device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol2, unsigned& state) {
   typedef Num<T> N_;
-  return make_rot_vals<T>(N_::real(G[p * JGP + p]), N_::real(G[q * JGP + q]), G[p * JGP + q], tol2, state);
+  return make_rot_vals<T>(N_::real(G[p * JGG + p]), N_::real(G[q * JGG + q]), G[p * JGG + q], tol2, state);
 }
 
 template <typename T> __device__ __forceinline__ T shfl_t(T v, int src);
@@ -213,6 +214,16 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   // s_nxt[step][a]: for rotation pair a of step + 1, the two pairs of `step` its columns come from and
   // on which side: byte 0 = pair of the smaller column, byte 1 = its side, byte 2 / 3 = same for the larger
   __shared__ unsigned int s_nxt[JB][JP / 2];
+  // s_gt[t] = (ta, tb), ta <= tb: the 136 blocks of the upper block triangle of G (16 x 16 blocks of 2 x 2)
+  __shared__ unsigned char s_gt[JB * (JB + 1) / 2][2];
+  if (tid < JB * JB) {
+    const int x = tid >> 4, y = tid & 15;
+    if (x <= y) {
+      const int t = x * JB - (x * (x - 1)) / 2 + (y - x);
+      s_gt[t][0] = (unsigned char)x;
+      s_gt[t][1] = (unsigned char)y;
+    }
+  }
   const int nsteps = a.diag ? JB - 1 : JB;
   if (tid < nsteps * (JP / 2)) {
     const int st_ = tid / (JP / 2), pr_ = tid % (JP / 2);
@@ -372,10 +383,10 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
 #pragma unroll
     for (int q = 1; q < 8; ++q) sum = N_::add(sum, part[q]);
     if (i == j) {
-      G[i * JGP + i] = N_::from(N_::real(sum), 0.0);
+      G[i * JGG + i] = N_::from(N_::real(sum), 0.0);
     } else {
-      G[i * JGP + j] = sum;
-      G[j * JGP + i] = N_::conj(sum);
+      G[i * JGG + j] = sum;
+      G[j * JGG + i] = N_::conj(sum);
     }
   }
   cluster.sync();  // all remote reads done before any CTA overwrites its partials (or exits)
@@ -386,17 +397,34 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   __syncthreads();
 
   // ---- parallel-ordered Jacobi rotations on G, accumulated in W --------------------------------------
-  // 16 (cross round) or 15 (diag round) steps of 16 disjoint rotations, one barrier per step:
-  //   warps 0..7  : thread (ta, tb) owns the 2 x 2 block of G between rotation pairs ta and tb
-  //                 (B' = J_a^H B J_b);
-  //   warps 8..14 : W' = W J_b on rows 2ta, 2ta+1 (256 tasks on 224 threads, warp 8 takes two);
-  //   warp 15     : builds the rotations of step s + 1 WHILE the others apply those of step s: the three
-  //                 entries of G^(s+1) a rotation needs follow from three 2 x 2 blocks of G^(s) and the
-  //                 two rotations of step s that touch its columns (rotated_entry).  The long dependent
-  //                 chain of make_rot (two rsqrt) is thereby off the critical path of the step.
+  // 16 (cross round) or 15 (diag round) steps of 16 disjoint rotations, one barrier per step.  Non-tensor
+  // FP64 instructions are the scarce resource here (measured: ~7 issue cycles per FP64 warp instruction on
+  // the busiest SM sub-partition decide the length of a step; warp w runs on sub-partition w & 3), hence:
+  //   warp 15 builds the rotations of step s + 1 WHILE the others apply those of step s: the three entries
+  //     of G^(s+1) a rotation needs follow from three 2 x 2 blocks of G^(s) and the two rotations of step s
+  //     that touch its columns (rotated_entry);
+  //   G' = J^H G J is Hermitian: warps 0, 4, 1, 5, 2 own the 136 blocks ta <= tb (thread = one 2 x 2 block,
+  //     B' = J_a^H B J_b) and store the mirror image too (G's pitch of 33 makes column stores conflict-free);
+  //   W' = W J acts on rows independently: with S = 2, 4 or 8 CTAs in the cluster each CTA only carries
+  //     32 / S rows of W through the steps (thread = rows 2wa, 2wa+1 x columns of pair wb); the last step
+  //     writes its rows into every CTA of the cluster (distributed shared memory), one cluster barrier follows.
   // G and W ping-pong between two buffers, the rotations between s_rc/s_rsp[0] and [1].
   constexpr int ROTW = JT / 32 - 1;
-  const int ta = (tid & 255) >> 4, tb = tid & 15;
+  constexpr int NGB = JB * (JB + 1) / 2;   // 136 blocks
+  const bool wsplit = (S > 1) && (JP % S == 0) && (S <= JP / 2);
+  const int w_rowpairs = wsplit ? (JP / 2) / S : JP / 2;   // row pairs of W carried by this CTA
+  const int w_first = wsplit ? crank * w_rowpairs : 0;
+  const int w_tasks = w_rowpairs * (JP / 2);
+  // role of this warp: G tasks [g0, g0 + 32) or W tasks [w0, w0 + 32), or nothing
+  int g0 = -1, w0 = -1;
+  {
+    const int g_warp[5] = {0, 4, 1, 5, 2};
+    const int w_warp[8] = {6, 10, 14, 3, 8, 9, 7, 12};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) if (warp == g_warp[i]) g0 = 32 * i;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (warp == w_warp[i] && 32 * i < w_tasks) w0 = 32 * i;
+  }
   const double tol2 = a.tol * a.tol;
   unsigned state = 0;
   __shared__ double s_rc[2][JP / 2];
@@ -425,58 +453,78 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         Rot<T> R1, R2;
         R1.c = s_rc[cur][a1]; R1.sp = s_rsp[cur][a1];
         R2.c = s_rc[cur][a2]; R2.sp = s_rsp[cur][a2];
-        const T al = rotated_entry<T>(Gc[p1 * JGP + p1], Gc[p1 * JGP + q1], Gc[q1 * JGP + p1], Gc[q1 * JGP + q1], R1, R1, r1, r1);
-        const T be = rotated_entry<T>(Gc[p2 * JGP + p2], Gc[p2 * JGP + q2], Gc[q2 * JGP + p2], Gc[q2 * JGP + q2], R2, R2, r2, r2);
-        const T ga = rotated_entry<T>(Gc[p1 * JGP + p2], Gc[p1 * JGP + q2], Gc[q1 * JGP + p2], Gc[q1 * JGP + q2], R1, R2, r1, r2);
+        const T al = rotated_entry<T>(Gc[p1 * JGG + p1], Gc[p1 * JGG + q1], Gc[q1 * JGG + p1], Gc[q1 * JGG + q1], R1, R1, r1, r1);
+        const T be = rotated_entry<T>(Gc[p2 * JGG + p2], Gc[p2 * JGG + q2], Gc[q2 * JGG + p2], Gc[q2 * JGG + q2], R2, R2, r2, r2);
+        const T ga = rotated_entry<T>(Gc[p1 * JGG + p2], Gc[p1 * JGG + q2], Gc[q1 * JGG + p2], Gc[q1 * JGG + q2], R1, R2, r1, r2);
         const Rot<T> r = make_rot_vals<T>(N_::real(al), N_::real(be), ga, tol2, state);
         s_rc[cur ^ 1][lane] = r.c;
         s_rsp[cur ^ 1][lane] = r.sp;
       }
       JSTAMP(2 + 4 * step, lane == 0);
-    } else if (warp < 8) {
-      const int pa = s_rr[step][ta][0], qa = s_rr[step][ta][1];
-      const int pb = s_rr[step][tb][0], qb = s_rr[step][tb][1];
-      Rot<T> Ra, Rb;
-      Ra.c = s_rc[cur][ta]; Ra.sp = s_rsp[cur][ta];
-      Rb.c = s_rc[cur][tb]; Rb.sp = s_rsp[cur][tb];
-      const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));  // -conj(sp_b)
-      const T b00 = Gc[pa * JGP + pb], b01 = Gc[pa * JGP + qb], b10 = Gc[qa * JGP + pb], b11 = Gc[qa * JGP + qb];
-      // T1 = B J_b:  T1[:,0] = c B[:,0] - conj(sp) B[:,1],  T1[:,1] = sp B[:,0] + c B[:,1]
-      const T t00 = rot_mix(Rb.c, b00, msb, b01), t01 = rot_mix(Rb.c, b01, Rb.sp, b00);
-      const T t10 = rot_mix(Rb.c, b10, msb, b11), t11 = rot_mix(Rb.c, b11, Rb.sp, b10);
-      // B' = J_a^H T1,  J_a^H = [[c, -sp], [conj(sp), c]]
-      const T msa = N_::sub(N_::zero(), Ra.sp), csa = N_::conj(Ra.sp);
-      T n00 = rot_mix(Ra.c, t00, msa, t10), n01 = rot_mix(Ra.c, t01, msa, t11);
-      T n10 = rot_mix(Ra.c, t10, csa, t00), n11 = rot_mix(Ra.c, t11, csa, t01);
-      if (ta == tb) {
-        // diagonal block: real diagonal, exact zero where a rotation was applied
-        n00 = N_::from(N_::real(n00), 0.0);
-        n11 = N_::from(N_::real(n11), 0.0);
-        if (Ra.c != 1.0 || N_::abs2(Ra.sp) != 0.0) { n01 = N_::zero(); n10 = N_::zero(); }
+    } else if (g0 >= 0) {
+      const int t = g0 + lane;
+      if (t < NGB) {
+        const int ta = s_gt[t][0], tb = s_gt[t][1];
+        const int pa = s_rr[step][ta][0], qa = s_rr[step][ta][1];
+        const int pb = s_rr[step][tb][0], qb = s_rr[step][tb][1];
+        Rot<T> Ra, Rb;
+        Ra.c = s_rc[cur][ta]; Ra.sp = s_rsp[cur][ta];
+        Rb.c = s_rc[cur][tb]; Rb.sp = s_rsp[cur][tb];
+        const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));  // -conj(sp_b)
+        const T b00 = Gc[pa * JGG + pb], b01 = Gc[pa * JGG + qb], b10 = Gc[qa * JGG + pb], b11 = Gc[qa * JGG + qb];
+        // T1 = B J_b:  T1[:,0] = c B[:,0] - conj(sp) B[:,1],  T1[:,1] = sp B[:,0] + c B[:,1]
+        const T t00 = rot_mix(Rb.c, b00, msb, b01), t01 = rot_mix(Rb.c, b01, Rb.sp, b00);
+        const T t10 = rot_mix(Rb.c, b10, msb, b11), t11 = rot_mix(Rb.c, b11, Rb.sp, b10);
+        // B' = J_a^H T1,  J_a^H = [[c, -sp], [conj(sp), c]]
+        const T msa = N_::sub(N_::zero(), Ra.sp), csa = N_::conj(Ra.sp);
+        T n00 = rot_mix(Ra.c, t00, msa, t10), n01 = rot_mix(Ra.c, t01, msa, t11);
+        T n10 = rot_mix(Ra.c, t10, csa, t00), n11 = rot_mix(Ra.c, t11, csa, t01);
+        if (ta == tb) {
+          // diagonal block: real diagonal, exact zero where a rotation was applied
+          n00 = N_::from(N_::real(n00), 0.0);
+          n11 = N_::from(N_::real(n11), 0.0);
+          if (Ra.c != 1.0 || N_::abs2(Ra.sp) != 0.0) { n01 = N_::zero(); n10 = N_::zero(); }
+        } else {
+          Gn[pb * JGG + pa] = N_::conj(n00); Gn[qb * JGG + pa] = N_::conj(n01);
+          Gn[pb * JGG + qa] = N_::conj(n10); Gn[qb * JGG + qa] = N_::conj(n11);
+        }
+        Gn[pa * JGG + pb] = n00; Gn[pa * JGG + qb] = n01; Gn[qa * JGG + pb] = n10; Gn[qa * JGG + qb] = n11;
       }
-      Gn[pa * JGP + pb] = n00; Gn[pa * JGP + qb] = n01; Gn[qa * JGP + pb] = n10; Gn[qa * JGP + qb] = n11;
       JSTAMP(3 + 4 * step, tid == 0);
-    } else {
-      // W' = W J_b on rows 2wa, 2wa+1, columns of pair wb
-      const int r1_ = tid - 256;
-      for (int task = r1_; task < 256; task += 224) {
-        const int wa = task >> 4, wb = task & 15;
+    } else if (w0 >= 0) {
+      const int task = w0 + lane;
+      if (task < w_tasks) {
+        const int wa = w_first + (task >> 4), wb = task & 15;
         const int pb = s_rr[step][wb][0], qb = s_rr[step][wb][1];
         Rot<T> Rb;
         Rb.c = s_rc[cur][wb]; Rb.sp = s_rsp[cur][wb];
         const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));
         const T w00 = Wc[(2 * wa) * JGP + pb], w01 = Wc[(2 * wa) * JGP + qb];
         const T w10 = Wc[(2 * wa + 1) * JGP + pb], w11 = Wc[(2 * wa + 1) * JGP + qb];
-        Wn[(2 * wa) * JGP + pb] = rot_mix(Rb.c, w00, msb, w01);
-        Wn[(2 * wa) * JGP + qb] = rot_mix(Rb.c, w01, Rb.sp, w00);
-        Wn[(2 * wa + 1) * JGP + pb] = rot_mix(Rb.c, w10, msb, w11);
-        Wn[(2 * wa + 1) * JGP + qb] = rot_mix(Rb.c, w11, Rb.sp, w10);
+        const T v00 = rot_mix(Rb.c, w00, msb, w01), v01 = rot_mix(Rb.c, w01, Rb.sp, w00);
+        const T v10 = rot_mix(Rb.c, w10, msb, w11), v11 = rot_mix(Rb.c, w11, Rb.sp, w10);
+        Wn[(2 * wa) * JGP + pb] = v00;
+        Wn[(2 * wa) * JGP + qb] = v01;
+        Wn[(2 * wa + 1) * JGP + pb] = v10;
+        Wn[(2 * wa + 1) * JGP + qb] = v11;
+        if (wsplit && step == nsteps - 1) {
+          // last step: the final rows also go to the other CTAs of the cluster (they never touch these rows)
+          for (int q = 0; q < S; ++q) {
+            if (q == crank) continue;
+            T* Wr = cluster.map_shared_rank(Wn, q);
+            Wr[(2 * wa) * JGP + pb] = v00;
+            Wr[(2 * wa) * JGP + qb] = v01;
+            Wr[(2 * wa + 1) * JGP + pb] = v10;
+            Wr[(2 * wa + 1) * JGP + qb] = v11;
+          }
+        }
       }
-      JSTAMP(4 + 4 * step, tid == 256);
+      JSTAMP(4 + 4 * step, lane == 0 && w0 == 0);
     }
     __syncthreads();
   }
   JSTAMP(1 + 4 * nsteps, tid == 0);
+  if (wsplit) cluster.sync();  // every CTA's rows of the final W have arrived; nobody left before its rows were written
 #endif
 #ifndef TNB_EXP_SKIP_EIGEN
   W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
