@@ -326,14 +326,18 @@ def main():
     d2h = 0
     # pinned result buffers (the compressed MPS has the shapes of the device-timed result)
     out_pinned = [torch.empty(tuple(t.shape), dtype=torch.complex128).pin_memory() for t in phi]
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    def e2e_step():
         p2, H2 = upload()
         out = sweep(p2, H2)
         res = [t.data.get(out=buf) for t, buf in zip(out, out_pinned)]
         torch.cuda.synchronize()
-        d2h = sum(r.numel() * 16 for r in res)
+        return sum(r.numel() * 16 for r in res)
+
+    e2e_step()   # one untimed pass: the allocator has seen the upload / download pattern
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d2h = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
