@@ -260,8 +260,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]  # both levels print the version banner on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import tncontract_b200 as tn
