@@ -252,6 +252,11 @@ def test_qr_many_columns(cplx):
     v, _ = np.linalg.qr(rnd(rng, (160, 160), cplx))
     a = (u * np.logspace(0, -12, 160)[None, :]) @ v.conj().T
     check(a)
+    # moderate condition numbers: the second-pass Gram matrix leaves the neighbourhood of I where the
+    # first-order factor is used (|G - I| ~ eps cond^2), so both branches of the 64 x 64 kernel are exercised
+    for decades in (2, 4, 5):
+        a = (u * np.logspace(0, -decades, 160)[None, :]) @ v.conj().T
+        check(a, tol=1e-11)
 
 
 
