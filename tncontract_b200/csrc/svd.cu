@@ -62,6 +62,7 @@ constexpr int JP = 2 * JB;   // columns in a block pair
 constexpr int JT = 512;      // threads per CTA: 2 x (JP/2)^2 -- G blocks on the first half, W blocks on the second
 constexpr int JGP = JP + 4;  // pitch of W / Gram partials in shared memory (= 4 mod 8: conflict-free DMMA fragments)
 constexpr int JGG = JP + 1;  // pitch of G (rotation phase only): row AND column accesses are conflict-free
+constexpr int JWP = JP + 2;  // pitch of W (= 2 mod 8): the apply reads it transposed (fragment [k = p][m = q]) without conflicts
 constexpr int JPAD = 4;      // panel pitch = CH + JPAD for the same reason
 constexpr int MAX_SWEEPS = 60;
 
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   cluster.sync();  // all remote reads done before any CTA overwrites its partials (or exits)
   for (int idx = tid; idx < JP * JP; idx += JT) {
     const int i = idx / JP, j = idx - i * JP;
-    W[i * JGP + j] = (i == j) ? N_::one() : N_::zero();
+    W[i * JWP + j] = (i == j) ? N_::one() : N_::zero();
   }
   __syncthreads();
 
@@ -499,23 +500,23 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         Rot<T> Rb;
         Rb.c = s_rc[cur][wb]; Rb.sp = s_rsp[cur][wb];
         const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));
-        const T w00 = Wc[(2 * wa) * JGP + pb], w01 = Wc[(2 * wa) * JGP + qb];
-        const T w10 = Wc[(2 * wa + 1) * JGP + pb], w11 = Wc[(2 * wa + 1) * JGP + qb];
+        const T w00 = Wc[(2 * wa) * JWP + pb], w01 = Wc[(2 * wa) * JWP + qb];
+        const T w10 = Wc[(2 * wa + 1) * JWP + pb], w11 = Wc[(2 * wa + 1) * JWP + qb];
         const T v00 = rot_mix(Rb.c, w00, msb, w01), v01 = rot_mix(Rb.c, w01, Rb.sp, w00);
         const T v10 = rot_mix(Rb.c, w10, msb, w11), v11 = rot_mix(Rb.c, w11, Rb.sp, w10);
-        Wn[(2 * wa) * JGP + pb] = v00;
-        Wn[(2 * wa) * JGP + qb] = v01;
-        Wn[(2 * wa + 1) * JGP + pb] = v10;
-        Wn[(2 * wa + 1) * JGP + qb] = v11;
+        Wn[(2 * wa) * JWP + pb] = v00;
+        Wn[(2 * wa) * JWP + qb] = v01;
+        Wn[(2 * wa + 1) * JWP + pb] = v10;
+        Wn[(2 * wa + 1) * JWP + qb] = v11;
         if (wsplit && step == nsteps - 1) {
           // last step: the final rows also go to the other CTAs of the cluster (they never touch these rows)
           for (int q = 0; q < S; ++q) {
             if (q == crank) continue;
             T* Wr = cluster.map_shared_rank(Wn, q);
-            Wr[(2 * wa) * JGP + pb] = v00;
-            Wr[(2 * wa) * JGP + qb] = v01;
-            Wr[(2 * wa + 1) * JGP + pb] = v10;
-            Wr[(2 * wa + 1) * JGP + qb] = v11;
+            Wr[(2 * wa) * JWP + pb] = v00;
+            Wr[(2 * wa) * JWP + qb] = v01;
+            Wr[(2 * wa + 1) * JWP + pb] = v10;
+            Wr[(2 * wa + 1) * JWP + qb] = v11;
           }
         }
       }
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
 #endif
         T av[4], bv[2];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JGP + mt * 8 + gq];
+        for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JWP + mt * 8 + gq];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) bv[nt] = P[(k0 + tq) * pitch + cw + nt * 8 + gq];
         if constexpr (CPLX) {
