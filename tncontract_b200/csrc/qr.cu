@@ -763,10 +763,11 @@ constexpr int QR_NBO = 128;  // outer block: trailing updates and the explicit Q
 
 struct QrLayout {
   int64_t k, ldw, ldv, nouter;
-  size_t off_w, off_v, off_t, off_w1, off_w2, off_sc, off_sk, sk_bytes, off_p2, off_cb, off_bc, total;
+  size_t off_w, off_v, off_t, off_w1, off_w2, off_sc, off_sk, sk_bytes, off_p2, off_cb, off_bc, off_rt, total;
 };
 
-constexpr int QR_CB = 64;  // column block of the Gram-Schmidt path (qr_bcgs2)
+constexpr int QR_CB = 64;   // column block of the Gram-Schmidt path (qr_bcgs2)
+constexpr int QR_GB = 256;  // column group of its lagged second pass; also the pitch of its panel buffers
 
 static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
   QrLayout L;
@@ -786,9 +787,10 @@ static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
   // split-K scratch for the (jb x n2 x m) products: up to 16 partials of a 128 x wide block
   L.sk_bytes = (m >= 1024) ? align_up((size_t)16 * QR_NBO * wide * es) : 0;
   L.off_sk = o; o += L.sk_bytes;
-  L.off_p2 = o; o += align_up((size_t)m * QR_CB * es);    // qr_bcgs2: second panel buffer
-  L.off_cb = o; o += align_up((size_t)L.k * QR_CB * es);  // qr_bcgs2: [Q^H W; W^H W] of pass 2
-  L.off_bc = o; o += align_up((size_t)L.k * QR_CB * es);  // qr_bcgs2: [-C R^-1; R^-1] of the current pass
+  L.off_p2 = o; o += align_up((size_t)m * QR_GB * es);    // qr_bcgs2: second panel buffer
+  L.off_cb = o; o += align_up((size_t)L.k * QR_GB * es);  // qr_bcgs2: [Q^H W; W^H W] of the second pass
+  L.off_bc = o; o += align_up((size_t)L.k * QR_GB * es);  // qr_bcgs2: [-C R^-1; R^-1] of the current pass
+  L.off_rt = o; o += align_up((size_t)3 * QR_GB * QR_GB * es);  // qr_bcgs2: small factors
   L.total = o;
   return L;
 }
@@ -990,10 +992,41 @@ __global__ void scale_by_kernel(T* x, int64_t n, const double* s) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) x[i] = Num<T>::scale(x[i], f);
 }
 
+// G = I + E (n x n Hermitian, upper triangle read) with |E| <= tol entrywise  ->  R = I + U, Rinv = I - U,
+// U = striu(E) + diag(E)/2: the Cholesky factor and its inverse to O(|E|^2).  Any entry outside tol (or a
+// NaN) raises flag[0]; the outputs stay finite either way.  Plain grid-stride kernel, any n.
+template <typename T>
+__global__ void near_identity_kernel(const T* G, int64_t ldg, int64_t n, T* R, int64_t ldr, T* Rinv, int64_t ldri,
+                                     double tol, int* flag) {
+  typedef Num<T> N_;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += step) {
+    const int64_t i = idx / n, j = idx - i * n;
+    T r = N_::zero(), ri = N_::zero();
+    if (j > i) {
+      const T e = G[i * ldg + j];
+      if (!(N_::abs2(e) <= tol * tol)) bad = true;
+      else { r = e; ri = N_::sub(N_::zero(), e); }
+    } else if (j == i) {
+      const T g = G[i * ldg + i];
+      const T e = N_::sub(g, N_::one());
+      double h = 0.0;
+      if (!(N_::abs2(e) <= tol * tol)) bad = true;
+      else h = 0.5 * (N_::real(g) - 1.0);
+      r = N_::from(1.0 + h, 0.0);
+      ri = N_::from(1.0 - h, 0.0);
+    }
+    R[i * ldr + j] = r;
+    Rinv[i * ldri + j] = ri;
+  }
+  if (bad) flag[0] = 1;
+}
+
 // returns 0 on success, 1 when the device flag asks for the Householder path, < 0 on errors
 template <typename T>
 static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws,
-                    int scale_mode, double** scale_out, cudaStream_t st) {
+                    int scale_mode, double** scale_out, bool lagged, cudaStream_t st) {
   typedef Num<T> N_;
   const QrLayout L = qr_layout(dtype, m, n);
   char* base = (char*)ws;
@@ -1001,11 +1034,13 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   T* Wsc = (T*)(base + L.off_w);                      // scaled copy of the columns beyond k (wide matrices)
   T* Qb = Q ? (T*)Q : (T*)(base + L.off_v);           // m x k orthonormal factor
   const int64_t ldq = Q ? k : L.ldv;
-  T* P2 = (T*)(base + L.off_p2);                      // m x QR_CB
-  T* Sb = (T*)(base + L.off_cb);                      // k x QR_CB   [C2; G0] of pass 2
-  T* Bc = (T*)(base + L.off_bc);                      // k x QR_CB   [-C R^-1; R^-1]
-  T* R1 = (T*)(base + L.off_t);                       // two QR_CB x QR_CB matrices
-  T* R2 = R1 + QR_CB * QR_CB;
+  constexpr int64_t LDB = QR_GB;                      // pitch of P2, Sb, Bc and the small factors
+  T* P2 = (T*)(base + L.off_p2);                      // m x QR_GB
+  T* Sb = (T*)(base + L.off_cb);                      // k x QR_GB   [C2; G0] of the second pass
+  T* Bc = (T*)(base + L.off_bc);                      // k x QR_GB   [-C R^-1; R^-1]
+  T* R1 = (T*)(base + L.off_rt);                      // three QR_GB x QR_GB matrices
+  T* R2 = R1 + QR_GB * QR_GB;
+  T* Rt = R2 + QR_GB * QR_GB;
   T* Rg = (T*)R;
   void* sk = L.sk_bytes ? (void*)(base + L.off_sk) : nullptr;
   int* flag = (int*)(base + L.off_sc + 128);
@@ -1029,54 +1064,92 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ci_smem));
     configured = true;
   }
-  auto chol_inv = [&](const T* G, int64_t ldg, T* Rout, T* Rinv, double rel_floor, double abs_floor, int bj) -> int {
-    const double near_tol = (abs_floor > 0.0) ? 1e-8 : 0.0;  // second pass only
-    ProfScope prof(KC_QR_PANEL, st, (sizeof(T) == 16 ? 4.0 : 1.0) * 2.0 / 3.0 * (double)bj * bj * bj);
-    kern<<<1, CI_THREADS, ci_smem, st>>>(G, ldg, bj, Rout, QR_CB, Rinv, QR_CB, rel_floor, abs_floor, near_tol, flag);
+  // the small factor of a pass: G (ld ldg) -> Rout (ld ldr), R^-1 -> Rinv (ld LDB)
+  struct Factor { int kind; T* Rout; int64_t ldr; double rel_floor, abs_floor, near_tol; };
+  auto factorise = [&](const Factor& f, const T* G, int64_t ldg, T* Rinv, int64_t b) -> int {
+    ProfScope prof(KC_QR_PANEL, st, (sizeof(T) == 16 ? 4.0 : 1.0) * 2.0 / 3.0 * (double)b * b * b);
+    if (f.kind == 0) {
+      kern<<<1, CI_THREADS, ci_smem, st>>>(G, ldg, (int)b, f.Rout, f.ldr, Rinv, LDB, f.rel_floor, f.abs_floor, f.near_tol, flag);
+    } else {
+      near_identity_kernel<T><<<blocks_for(b * b), 256, 0, st>>>(G, ldg, b, f.Rout, f.ldr, Rinv, LDB, f.near_tol, flag);
+    }
     TNB_LAUNCH_CHECK();
     ++g_launches;
     return 0;
   };
   int rc;
-  // one pass: S (ld lds) <- [Qj, W]^H W;  G in place;  Rout, Bc;  P2 <- [Qj, W] Bc;  W <- P2
-  auto pass = [&](int64_t j0, int64_t bj, T* Qp, T* S, int64_t lds, T* Rout, double rel_floor, double abs_floor) -> int {
-    const int64_t kk = j0 + bj;
-    int r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, kk, bj, m, 1, 0, Qb, ldq, 0, Qp, ldq, 0, 0, 0, S, lds, 0, 1, sk, L.sk_bytes, st);
+  // one pass over the panel Qp = Q[:, j0 : j0 + b]:
+  //   S (ld lds) <- [Qj, W]^H W;  G = G0 - C^H C in place;  factor;  Bc = [-C R^-1; R^-1];  W <- [Qj, W] Bc
+  auto pass = [&](int64_t j0, int64_t b, T* Qp, T* S, int64_t lds, const Factor& f) -> int {
+    const int64_t kk = j0 + b;
+    int r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, kk, b, m, 1, 0, Qb, ldq, 0, Qp, ldq, 0, 0, 0, S, lds, 0, 1, sk, L.sk_bytes, st);
     if (r_) return r_;
     T* G = S + j0 * lds;
-    T* Ri = Bc + j0 * QR_CB;
+    T* Ri = Bc + j0 * LDB;
     if (j0 > 0) {
-      r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, bj, bj, j0, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, L.sk_bytes, st);
+      r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, b, b, j0, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, L.sk_bytes, st);
       if (r_) return r_;
     }
-    chol_inv(G, lds, Rout, Ri, rel_floor, abs_floor, (int)bj);
+    factorise(f, G, lds, Ri, b);
     if (j0 > 0) {
-      r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, bj, bj, -1, 0, S, lds, 0, Ri, QR_CB, 0, 0, 0, Bc, QR_CB, 0, 1, st);
+      r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, b, b, -1, 0, S, lds, 0, Ri, LDB, 0, 0, 0, Bc, LDB, 0, 1, st);
       if (r_) return r_;
     }
-    r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, bj, kk, 1, 0, Qb, ldq, 0, Bc, QR_CB, 0, 0, 0, P2, QR_CB, 0, 1, sk, L.sk_bytes, st);
+    r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, kk, 1, 0, Qb, ldq, 0, Bc, LDB, 0, 0, 0, P2, LDB, 0, 1, sk, L.sk_bytes, st);
     if (r_) return r_;
-    copy2d_kernel<T><<<blocks_for(m * bj), 256, 0, st>>>(P2, QR_CB, Qp, ldq, m, bj, nullptr);
+    copy2d_kernel<T><<<blocks_for(m * b), 256, 0, st>>>(P2, LDB, Qp, ldq, m, b, nullptr);
     TNB_LAUNCH_CHECK();
     return 0;
   };
-  for (int64_t j0 = 0; j0 < k; j0 += QR_CB) {
-    const int64_t bj = (k - j0 < QR_CB) ? (k - j0) : QR_CB;
-    T* Qp = Qb + j0;
-    T* Rj = Rg + j0;                // R[0:j0, J], ld n  (pass 1 leaves C1 there, and G0 -> G in R[J, J])
-    T* Rjj = Rg + j0 * n + j0;
-    copy2d_kernel<T><<<blocks_for(m * bj), 256, 0, st>>>((const T*)A + j0, lda, Qp, ldq, m, bj, sc);
-    TNB_LAUNCH_CHECK();
-    rc = pass(j0, bj, Qp, Rj, n, R1, 1e-10, 0.0);
-    if (rc) return rc;
-    rc = pass(j0, bj, Qp, Sb, QR_CB, R2, 0.0, 0.25);
-    if (rc) return rc;
-    if (j0 > 0) {  // R[:j0, J] = C1 + C2 R1
-      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, bj, bj, 1, 0, Sb, QR_CB, 0, R1, QR_CB, 0, 1, 0, Rj, n, 0, 1, st);
+  if (!lagged) {
+    // two passes per 64-column block
+    for (int64_t j0 = 0; j0 < k; j0 += QR_CB) {
+      const int64_t bj = (k - j0 < QR_CB) ? (k - j0) : QR_CB;
+      T* Qp = Qb + j0;
+      T* Rj = Rg + j0;                // R[0:j0, J], ld n  (pass 1 leaves C1 there, and G0 -> G in R[J, J])
+      T* Rjj = Rg + j0 * n + j0;
+      copy2d_kernel<T><<<blocks_for(m * bj), 256, 0, st>>>((const T*)A + j0, lda, Qp, ldq, m, bj, sc);
+      TNB_LAUNCH_CHECK();
+      rc = pass(j0, bj, Qp, Rj, n, Factor{0, R1, LDB, 1e-10, 0.0, 0.0});
+      if (rc) return rc;
+      rc = pass(j0, bj, Qp, Sb, LDB, Factor{0, R2, LDB, 0.0, 0.25, 1e-8});
+      if (rc) return rc;
+      if (j0 > 0) {  // R[:j0, J] = C1 + C2 R1
+        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, bj, bj, 1, 0, Sb, LDB, 0, R1, LDB, 0, 1, 0, Rj, n, 0, 1, st);
+        if (rc) return rc;
+      }
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, bj, bj, bj, 1, 0, R2, LDB, 0, R1, LDB, 0, 0, 0, Rjj, n, 0, 1, st);
       if (rc) return rc;
     }
-    rc = gemm(dtype, TNB_OP_N, TNB_OP_N, bj, bj, bj, 1, 0, R2, QR_CB, 0, R1, QR_CB, 0, 0, 0, Rjj, n, 0, 1, st);
-    if (rc) return rc;
+  } else {
+    // Lagged reorthogonalisation: the first pass runs block by block (64 columns, Cholesky in the small
+    // kernel, R1 and the couplings C1 land directly in R); the second pass runs once per GROUP of 256
+    // columns.  After one pass the group is orthonormal to ~eps cond^2, so its Gram matrix against
+    // [earlier groups, itself] is I + E with tiny E and the first-order factor R2 = I + U serves for any
+    // width -- a quarter of the second-pass launches, and GEMMs with N = 256.  |E| > 1e-8 anywhere raises the
+    // flag (the caller then repeats the factorisation with two passes per block).
+    for (int64_t g0 = 0; g0 < k; g0 += QR_GB) {
+      const int64_t bg = (k - g0 < QR_GB) ? (k - g0) : QR_GB;
+      copy2d_kernel<T><<<blocks_for(m * bg), 256, 0, st>>>((const T*)A + g0, lda, Qb + g0, ldq, m, bg, sc);
+      TNB_LAUNCH_CHECK();
+      for (int64_t j0 = g0; j0 < g0 + bg; j0 += QR_CB) {
+        const int64_t bj = (g0 + bg - j0 < QR_CB) ? (g0 + bg - j0) : QR_CB;
+        rc = pass(j0, bj, Qb + j0, Rg + j0, n, Factor{0, Rg + j0 * n + j0, n, 1e-10, 0.0, 0.0});
+        if (rc) return rc;
+      }
+      rc = pass(g0, bg, Qb + g0, Sb, LDB, Factor{1, R2, LDB, 0.0, 0.0, 1e-8});
+      if (rc) return rc;
+      // R[G, G] = R2 R1g,  R[:g0, G] = C1 + C2 R1g   (R1g = the group's first-pass factor, now in R[G, G])
+      T* Rgg = Rg + g0 * n + g0;
+      copy2d_kernel<T><<<blocks_for(bg * bg), 256, 0, st>>>(Rgg, n, Rt, LDB, bg, bg, nullptr);
+      TNB_LAUNCH_CHECK();
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, bg, bg, bg, 1, 0, R2, LDB, 0, Rt, LDB, 0, 0, 0, Rgg, n, 0, 1, st);
+      if (rc) return rc;
+      if (g0 > 0) {
+        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, g0, bg, bg, 1, 0, Sb, LDB, 0, Rt, LDB, 0, 1, 0, Rg + g0, n, 0, 1, st);
+        if (rc) return rc;
+      }
+    }
   }
   if (n > k) {  // wide: R[:, k:] = Q^H (scale * A[:, k:])
     copy2d_kernel<T><<<blocks_for(m * (n - k)), 256, 0, st>>>((const T*)A + k, lda, Wsc, L.ldw, m, n - k, sc);
@@ -1213,15 +1286,19 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
 
 // internal entry used by svd.cu as well
 // kernel experiments: TNB_QR_BCGS=0 forces the Householder path everywhere
-static const int g_qr_bcgs = getenv("TNB_QR_BCGS") ? atoi(getenv("TNB_QR_BCGS")) : 1;
+static const int g_qr_bcgs = getenv("TNB_QR_BCGS") ? atoi(getenv("TNB_QR_BCGS")) : 2;
 
 int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, int scale_mode,
        double** scale_out, cudaStream_t st) {
   // many columns: Gram-Schmidt path (all GEMMs); falls back to Householder when its device checks trip
   const int64_t k = m < n ? m : n;
   if (g_qr_bcgs && R && k >= 2 * QR_CB) {
-    const int rc = (dtype == TNB_F64) ? qr_bcgs2<double>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st)
-                                      : qr_bcgs2<cplx>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st);
+    int rc = 1;
+    // first the lagged second pass (TNB_QR_BCGS >= 2, the default), then two passes per block, then Householder
+    for (int lag = (g_qr_bcgs >= 2 && k > 2 * QR_CB) ? 1 : 0; lag >= 0 && rc == 1; --lag) {
+      rc = (dtype == TNB_F64) ? qr_bcgs2<double>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, lag != 0, st)
+                              : qr_bcgs2<cplx>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, lag != 0, st);
+    }
     if (rc <= 0) return rc;
   }
   if (dtype == TNB_F64) return qr_impl<double>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, st);
