@@ -992,6 +992,25 @@ __global__ void scale_by_kernel(T* x, int64_t n, const double* s) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) x[i] = Num<T>::scale(x[i], f);
 }
 
+// Side stream + events of qr_bcgs2 (the projection W - Q C of a first pass runs next to the 64 x 64 Cholesky
+// kernel), one set per host thread and device (batch.py drives several streams from several host threads).
+struct QrSide {
+  int dev = -1;
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int get(int device) {
+    if (dev == device && s) return 0;
+    TNB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    TNB_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    TNB_CUDA_CHECK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    dev = device;
+    return 0;
+  }
+};
+static thread_local QrSide g_qr_side;
+// kernel experiments: TNB_QR_OVERLAP=0 keeps everything on the caller's stream
+static const int g_qr_overlap = getenv("TNB_QR_OVERLAP") ? atoi(getenv("TNB_QR_OVERLAP")) : 1;
+
 // G = I + E (n x n Hermitian, upper triangle read) with |E| <= tol entrywise  ->  R = I + U, Rinv = I - U,
 // U = striu(E) + diag(E)/2: the Cholesky factor and its inverse to O(|E|^2).  Any entry outside tol (or a
 // NaN) raises flag[0]; the outputs stay finite either way.  Plain grid-stride kernel, any n.
@@ -1043,6 +1062,20 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   T* Rt = R2 + QR_GB * QR_GB;
   T* Rg = (T*)R;
   void* sk = L.sk_bytes ? (void*)(base + L.off_sk) : nullptr;
+  // first pass of the lagged scheme: W - Q C on a side stream next to the Cholesky kernel; the side GEMM gets
+  // the last quarter of the split-K scratch, which also keeps its grid below one wave (an SM stays free for
+  // the single-CTA Cholesky kernel)
+  const bool overlap = lagged && g_qr_overlap && L.sk_bytes > 0;
+  const size_t sk_main = overlap ? ((L.sk_bytes / 4) * 3) & ~(size_t)255 : L.sk_bytes;
+  void* sk_side = overlap ? (void*)(base + L.off_sk + sk_main) : nullptr;
+  const size_t sk_side_bytes = overlap ? L.sk_bytes - sk_main : 0;
+  QrSide& side = g_qr_side;
+  if (overlap) {
+    int device = 0;
+    TNB_CUDA_CHECK(cudaGetDevice(&device));
+    const int rs = side.get(device);
+    if (rs) return rs;
+  }
   int* flag = (int*)(base + L.off_sc + 128);
   double* sc = nullptr;
   if (scale_mode != 0) {
@@ -1082,21 +1115,38 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   //   S (ld lds) <- [Qj, W]^H W;  G = G0 - C^H C in place;  factor;  Bc = [-C R^-1; R^-1];  W <- [Qj, W] Bc
   auto pass = [&](int64_t j0, int64_t b, T* Qp, T* S, int64_t lds, const Factor& f) -> int {
     const int64_t kk = j0 + b;
-    int r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, kk, b, m, 1, 0, Qb, ldq, 0, Qp, ldq, 0, 0, 0, S, lds, 0, 1, sk, L.sk_bytes, st);
+    int r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, kk, b, m, 1, 0, Qb, ldq, 0, Qp, ldq, 0, 0, 0, S, lds, 0, 1, sk, sk_main, st);
     if (r_) return r_;
     T* G = S + j0 * lds;
     T* Ri = Bc + j0 * LDB;
+    const bool fork = overlap && f.kind == 0 && j0 > 0;
+    if (fork) {
+      // side stream: W <- W - Qj C in place (C is complete; the Cholesky does not need W)
+      TNB_CUDA_CHECK(cudaEventRecord(side.fork, st));
+      TNB_CUDA_CHECK(cudaStreamWaitEvent(side.s, side.fork, 0));
+    }
     if (j0 > 0) {
-      r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, b, b, j0, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, L.sk_bytes, st);
+      r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, b, b, j0, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, sk_main, st);
       if (r_) return r_;
     }
     factorise(f, G, lds, Ri, b);
-    if (j0 > 0) {
-      r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, b, b, -1, 0, S, lds, 0, Ri, LDB, 0, 0, 0, Bc, LDB, 0, 1, st);
+    if (fork) {
+      r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, j0, -1, 0, Qb, ldq, 0, S, lds, 0, 1, 0, Qp, ldq, 0, 1, sk_side, sk_side_bytes,
+                   side.s);
+      TNB_CUDA_CHECK(cudaEventRecord(side.join, side.s));
+      TNB_CUDA_CHECK(cudaStreamWaitEvent(st, side.join, 0));
+      if (r_) return r_;
+      // W <- (W - Qj C) R^-1
+      r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, m, b, b, 1, 0, Qp, ldq, 0, Ri, LDB, 0, 0, 0, P2, LDB, 0, 1, st);
+      if (r_) return r_;
+    } else {
+      if (j0 > 0) {
+        r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, b, b, -1, 0, S, lds, 0, Ri, LDB, 0, 0, 0, Bc, LDB, 0, 1, st);
+        if (r_) return r_;
+      }
+      r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, kk, 1, 0, Qb, ldq, 0, Bc, LDB, 0, 0, 0, P2, LDB, 0, 1, sk, sk_main, st);
       if (r_) return r_;
     }
-    r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, kk, 1, 0, Qb, ldq, 0, Bc, LDB, 0, 0, 0, P2, LDB, 0, 1, sk, L.sk_bytes, st);
-    if (r_) return r_;
     copy2d_kernel<T><<<blocks_for(m * b), 256, 0, st>>>(P2, LDB, Qp, ldq, m, b, nullptr);
     TNB_LAUNCH_CHECK();
     return 0;
@@ -1154,7 +1204,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   if (n > k) {  // wide: R[:, k:] = Q^H (scale * A[:, k:])
     copy2d_kernel<T><<<blocks_for(m * (n - k)), 256, 0, st>>>((const T*)A + k, lda, Wsc, L.ldw, m, n - k, sc);
     TNB_LAUNCH_CHECK();
-    rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, k, n - k, m, 1, 0, Qb, ldq, 0, Wsc, L.ldw, 0, 0, 0, Rg + k, n, 0, 1, sk, L.sk_bytes, st);
+    rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, k, n - k, m, 1, 0, Qb, ldq, 0, Wsc, L.ldw, 0, 0, 0, Rg + k, n, 0, 1, sk, sk_main, st);
     if (rc) return rc;
   }
   if (scale_mode == 1) {
