@@ -1066,7 +1066,8 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   // the last quarter of the split-K scratch, which also keeps its grid below one wave (an SM stays free for
   // the single-CTA Cholesky kernel)
   const bool overlap = lagged && g_qr_overlap && L.sk_bytes > 0;
-  const size_t sk_main = overlap ? ((L.sk_bytes / 4) * 3) & ~(size_t)255 : L.sk_bytes;
+  static const int side_pct = getenv("TNB_QR_SIDE_PCT") ? atoi(getenv("TNB_QR_SIDE_PCT")) : 20;  // kernel experiments
+  const size_t sk_main = overlap ? ((L.sk_bytes / 100) * (100 - side_pct)) & ~(size_t)255 : L.sk_bytes;
   void* sk_side = overlap ? (void*)(base + L.off_sk + sk_main) : nullptr;
   const size_t sk_side_bytes = overlap ? L.sk_bytes - sk_main : 0;
   QrSide& side = g_qr_side;
