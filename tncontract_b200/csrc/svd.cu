@@ -23,20 +23,25 @@
 //     into chunks of CH elements; each CTA of the cluster owns chunks
 //     crank, crank+S, ... and keeps the last Xt chunk it read resident in
 //     shared memory;
-//   * each CTA forms the partial 32 x 32 Gram matrix of its Xt chunks, the
-//     partials are summed through distributed shared memory (two cluster
-//     barriers, identical summation order everywhere, so every CTA holds the
-//     same bits);
+//   * each CTA forms the partial 32 x 32 Gram matrix of its Xt chunks -- Hermitian:
+//     only the 10 upper 8 x 8 tiles, complex products in the 3-multiplication
+//     form (3 DMMAs instead of 4) -- and the partials are summed through
+//     distributed shared memory (two cluster barriers, identical summation
+//     order everywhere, so every CTA holds the same bits);
 //   * every CTA runs the same parallel-ordered two-sided Jacobi steps on the
-//     Gram matrix in shared memory (16 or 15 steps of 16 disjoint rotations,
-//     thread (a, b) owns the 2 x 2 block between rotation pairs a and b), which
-//     yields the 32 x 32 unitary W of accumulated rotations; the rotation
-//     angles are exactly those of one-sided Jacobi on the columns;
-//   * every CTA applies W to its chunks (rows_new = W^T rows) and stores them.
-// Convergence: the largest |x_p^H x_q| / (|x_p||x_q|) seen before rotating is
-// accumulated with atomicMax; a one-thread kernel closes each sweep and sets a
-// device flag that turns the remaining queued launches into no-ops, so the
-// host only synchronises every few sweeps.  tol = sqrt(k) * eps (as LAPACK's
+//     Gram matrix in shared memory (16 or 15 steps of 16 disjoint rotations):
+//     one warp builds the rotations of step s + 1 while five warps update the
+//     136 upper 2 x 2 blocks of G for step s and two warps carry this CTA's
+//     share of the rows of the accumulated 32 x 32 unitary W (the rows are
+//     split over the cluster and exchanged once, in the last step); the
+//     rotation angles are exactly those of one-sided Jacobi on the columns;
+//   * every CTA applies W to its chunks (rows_new = W^T rows, DMMA) and stores
+//     them by TMA.
+// Convergence: every rotation records whether its cosine |x_p^H x_q| / (|x_p||x_q|)
+// exceeded tol and whether it exceeded 1e-7 (atomicOr on a device word); a
+// one-thread kernel closes each sweep and sets a device flag that turns the
+// remaining queued launches into no-ops, so the host only synchronises every
+// few sweeps.  tol = sqrt(k) * eps (as LAPACK's
 // xGESVJ).  HBM/L2 traffic per round: Xt and Vt read once and written once.
 #include <cooperative_groups.h>
 #include <math.h>
@@ -151,14 +156,6 @@ template <typename T>
 __device__ __forceinline__ Rot<T> make_rot(const T* G, int p, int q, double tol2, unsigned& state) {
   typedef Num<T> N_;
   return make_rot_vals<T>(N_::real(G[p * JGG + p]), N_::real(G[q * JGG + q]), G[p * JGG + q], tol2, state);
-}
-
-template <typename T> __device__ __forceinline__ T shfl_t(T v, int src);
-template <> __device__ __forceinline__ double shfl_t<double>(double v, int src) {
-  return __shfl_sync(0xffffffffu, v, src);
-}
-template <> __device__ __forceinline__ cplx shfl_t<cplx>(cplx v, int src) {
-  return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
 
 // c * x + s * y  (c real, s complex or real), written as FMA chains
