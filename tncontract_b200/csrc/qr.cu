@@ -1,18 +1,25 @@
 // Reduced QR factorisation (np.linalg.qr(mode="reduced"), reference call site
-// tensor.py:1044) for float64 / complex128, LAPACK geqrf/ungqr conventions:
-// H_j = I - tau_j v_j v_j^H, R = H_k^H ... H_1^H A with a REAL diagonal,
-// Q = H_1 ... H_k [I; 0].
+// tensor.py:1044) for float64 / complex128: A = Q R, Q with orthonormal columns,
+// R upper triangular (trapezoidal for m < n) with a REAL diagonal.
 //
-// Blocked Householder with compact-WY updates:
-//   * panel (NB = 32 columns): ONE thread-block cluster owns the whole panel in
-//     shared memory, rows split across the CTAs of the cluster.  Per column the
-//     only communication is one all-reduce of the NB partial dot products
-//     x^H A[:, c] (from which norm, tau, and v^H A[:, c] all follow), exchanged
-//     through distributed shared memory with one cluster barrier -- no global
-//     memory round trip, no grid-wide sync.  The panel also emits V (explicit,
-//     unit lower trapezoid) and the triangular factor T of the block reflector.
-//   * trailing matrix / explicit Q: three GEMMs per panel on the FP64 tensor
-//     pipe (gemm.cu): W = V^H A2, W = T^H W, A2 -= V W.
+// Two paths, chosen in qr():
+//   * k = min(m, n) >= 128: block Gram-Schmidt with reorthogonalisation
+//     (BCGS-PIP+, qr_bcgs2 below): every O(m n^2) operation is a DMMA GEMM over
+//     all SMs, the only serial kernel is a 64 x 64 Cholesky + triangular inverse
+//     per column block; the second pass is lagged to groups of 256 columns and
+//     needs no Cholesky at all (first-order factor of a near-identity Gram
+//     matrix); device checks fall back to the path below.
+//   * otherwise, and as the fallback: blocked Householder with compact-WY
+//     updates (LAPACK geqrf/ungqr conventions: H_j = I - tau_j v_j v_j^H,
+//     R = H_k^H ... H_1^H A, Q = H_1 ... H_k [I; 0]):
+//       - panel (NB = 32 columns): ONE thread-block cluster owns the whole panel
+//         in shared memory, rows split across the CTAs of the cluster
+//         (CholeskyQR2 + Householder reconstruction, or column-by-column
+//         Householder with one DSMEM all-reduce per column for ill-conditioned
+//         panels).  The panel also emits V (explicit, unit lower trapezoid) and
+//         the triangular factor T of the block reflector.
+//       - trailing matrix / explicit Q: three GEMMs per 128-column outer block on
+//         the FP64 tensor pipe (gemm.cu): W = V^H A2, W = T^H W, A2 -= V W.
 // Nominal flops (LAPACK model): 2(2mn^2 - 2/3 n^3) real, x4 complex.
 #include <cooperative_groups.h>
 #include <stdlib.h>
