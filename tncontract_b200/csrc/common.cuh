@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/tnb.h"
 
 #define TNB_CUDA_CHECK(expr)                         \
@@ -14,10 +16,13 @@
 
 // every kernel launch of the library goes through this macro, so the counter
 // is the number of libtnb kernels launched (bench.py reports it as gpu_launches)
-namespace tnb { extern long long g_launches; }
+namespace tnb {
+extern std::atomic<long long> g_launches;   // several host threads may drive the library (one stream each)
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}
 #define TNB_LAUNCH_CHECK()                   \
   do {                                       \
-    ++tnb::g_launches;                       \
+    tnb::count_launch();                     \
     TNB_CUDA_CHECK(cudaGetLastError());      \
   } while (0)
 
@@ -59,6 +64,7 @@ __host__ __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.
 // Scalar traits so kernels can be written once for double and complex128.
 template <typename T> struct Num;
 template <> struct Num<double> {
+  typedef double real_t;
   static constexpr int dtype = TNB_F64;
   __host__ __device__ static double zero() { return 0.0; }
   __host__ __device__ static double one() { return 1.0; }
@@ -74,6 +80,7 @@ template <> struct Num<double> {
   __host__ __device__ static double fma(double x, double y, double a) { return a + x * y; }
 };
 template <> struct Num<cplx> {
+  typedef double real_t;
   static constexpr int dtype = TNB_C128;
   __host__ __device__ static cplx zero() { return make_double2(0.0, 0.0); }
   __host__ __device__ static cplx one() { return make_double2(1.0, 0.0); }
@@ -88,6 +95,36 @@ template <> struct Num<cplx> {
   __host__ __device__ static cplx fma_conj(cplx x, cplx y, cplx a) { return cfma_conj(x, y, a); }
   __host__ __device__ static cplx fma(cplx x, cplx y, cplx a) { return cfma(x, y, a); }
 };
+
+// Single-precision counterparts: used ONLY for the Gram-domain rotation phase of the Jacobi round (svd.cu), where the
+// data decides angles but never touches the matrix itself.
+template <> struct Num<float> {
+  typedef float real_t;
+  __host__ __device__ static float zero() { return 0.f; }
+  __host__ __device__ static float one() { return 1.f; }
+  __host__ __device__ static float conj(float a) { return a; }
+  __host__ __device__ static float add(float a, float b) { return a + b; }
+  __host__ __device__ static float sub(float a, float b) { return a - b; }
+  __host__ __device__ static float scale(float a, float s) { return a * s; }
+  __host__ __device__ static float abs2(float a) { return a * a; }
+  __host__ __device__ static float real(float a) { return a; }
+  __host__ __device__ static float from(float re, float) { return re; }
+};
+template <> struct Num<float2> {
+  typedef float real_t;
+  __host__ __device__ static float2 zero() { return make_float2(0.f, 0.f); }
+  __host__ __device__ static float2 one() { return make_float2(1.f, 0.f); }
+  __host__ __device__ static float2 conj(float2 a) { return make_float2(a.x, -a.y); }
+  __host__ __device__ static float2 add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+  __host__ __device__ static float2 sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+  __host__ __device__ static float2 scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+  __host__ __device__ static float abs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+  __host__ __device__ static float real(float2 a) { return a.x; }
+  __host__ __device__ static float2 from(float re, float im) { return make_float2(re, im); }
+};
+template <typename T> struct LowPrec;
+template <> struct LowPrec<double> { typedef float type; };
+template <> struct LowPrec<cplx> { typedef float2 type; };
 
 static inline size_t elem_size(int dtype) { return dtype == TNB_C128 ? 16 : 8; }
 
@@ -153,6 +190,12 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // waits only until the shared-memory SOURCE of every committed bulk store has been read (the buffer may
 // be reused, the CTA may exit); the global writes themselves complete by the end of the grid at the latest
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+
+// ---- programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization) ----
+// wait: the preceding grid of the stream has completed and its writes are visible; launch_dependents: the
+// next grid may be scheduled once every CTA of this one has executed it (or exited).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -325,8 +325,7 @@ extern "C" int tnb_truncation_count(const double* s, int64_t n, int64_t chi, dou
 
 extern "C" int tnb_version(void) { return 100; }
 extern "C" long long tnb_launch_count(int reset) {
-  const long long v = tnb::g_launches;
-  if (reset) tnb::g_launches = 0;
+  const long long v = reset ? tnb::g_launches.exchange(0) : tnb::g_launches.load();
   return v;
 }
 

@@ -17,16 +17,20 @@
 
 namespace tnb {
 
-long long g_launches = 0;
-static int g_sm_count = 0;
+std::atomic<long long> g_launches{0};
+// SM count of the CURRENT device, cached per device (a process may drive several GPUs, from several threads)
 int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
-  return g_sm_count;
+  return n;
 }
 
 struct PermParams {

@@ -23,7 +23,7 @@ static cudaEvent_t get_event() {
   return e;
 }
 
-ProfScope::ProfScope(int c, cudaStream_t s, double w) : cls(c), st(s), work(w), l0(g_launches), idx(-1) {
+ProfScope::ProfScope(int c, cudaStream_t s, double w) : cls(c), st(s), work(w), l0(g_launches.load()), idx(-1) {
   if (!g_prof_on) return;
   ProfRec r;
   r.cls = c; r.work = w; r.launches = 0;
@@ -36,7 +36,7 @@ ProfScope::ProfScope(int c, cudaStream_t s, double w) : cls(c), st(s), work(w), 
 ProfScope::~ProfScope() {
   if (idx < 0) return;
   ProfRec& r = g_recs[(size_t)idx];
-  r.launches = g_launches - l0;
+  r.launches = g_launches.load() - l0;
   r.work = work;
   cudaEventRecord(r.e1, st);
 }

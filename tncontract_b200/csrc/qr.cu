@@ -845,7 +845,7 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
   // panel factorisation + T factor: ~ (2 jb^2 + jb^2) mr real flops, x4 complex
   ProfScope prof(KC_QR_PANEL, st, (sizeof(T) == 16 ? 4.0 : 1.0) * 3.0 * (double)mr * a.jb * a.jb);
   TNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
-  ++g_launches;
+  count_launch();
   return 0;
 }
 
@@ -1115,7 +1115,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       near_identity_kernel<T><<<blocks_for(b * b), 256, 0, st>>>(G, ldg, b, f.Rout, f.ldr, Rinv, LDB, f.near_tol, flag);
     }
     TNB_LAUNCH_CHECK();
-    ++g_launches;
+    count_launch();
     return 0;
   };
   int rc;
