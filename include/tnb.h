@@ -66,9 +66,6 @@ long long tnb_launch_count(int reset);
 int tnb_profile_enable(int on);
 int tnb_profile_get(int cls, double* ms, double* work, long long* launches, long long* scopes);
 
-/* development aid: clock64 phase stamps of the last fast-path QR panel (TNB_QR_FAST_PANEL=3) */
-int tnb_debug_qr_stamps(long long* out, int n);
-
 /* ---- index permutation: np.rollaxis/np.transpose + np.reshape copy -------
  * replaces the materialised copies behind tensor.py:295,315,354,363,392-394,
  * 482,818,911,1041 and ndarray.copy()/conjugate() (tensor.py:378,485).

@@ -17,3 +17,7 @@ for s in range(16):
     nxt = t[b + 4] if s < 15 else t[65]
     print("step %2d: start +%6d | rot warp done +%5d | G warp0 done +%5d | W warp8 done +%5d | step length %5d" %
           (s, t[b] - t[0], t[b + 1] - t[b], t[b + 2] - t[b], t[b + 3] - t[b], nxt - t[b]))
+ph = ["entry", "prologue done", "griddep wait done", "load+Gram done", "reduction done", "rotation done", "apply+store done"]
+for i in range(1, 7):
+    print("%-20s +%6d cycles (%.2f us)" % (ph[i], t[70 + i] - t[70 + i - 1], (t[70 + i] - t[70 + i - 1]) / 1965.0))
+print("kernel body total %.2f us" % ((t[76] - t[70]) / 1965.0))

@@ -41,7 +41,6 @@ SIGNATURES = {
     "tnb_launch_count": (_c.c_longlong, [_c.c_int]),
     "tnb_profile_enable": (_c.c_int, [_c.c_int]),
     "tnb_profile_get": (_c.c_int, [_c.c_int, _pdbl, _pdbl, _c.POINTER(_c.c_longlong), _c.POINTER(_c.c_longlong)]),
-    "tnb_debug_qr_stamps": (_c.c_int, [_c.POINTER(_c.c_longlong), _c.c_int]),
     "tnb_permute": (_c.c_int, [_pd, _pi32, _vp, _dbl, _dbl, _c.c_int, _vp]),
     "tnb_scale_inplace": (_c.c_int, [_pd, _dbl, _dbl, _vp]),
     "tnb_axpby": (_c.c_int, [_pd, _pd, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),

@@ -252,4 +252,14 @@ static inline int64_t numel(const tnb_tensor_t* t) {
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
+// "This per-device function attribute has been set on the current device": one mark per device, safe against
+// concurrent first use from several host threads (setting an attribute twice is harmless, so a plain atomic
+// flag is enough).  Usage:  static PerDeviceOnce once;  if (once.need()) { cudaFuncSetAttribute(...); once.done(); }
+struct PerDeviceOnce {
+  std::atomic<int> mark[64];
+  static int dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < 64) ? d : 0; }
+  bool need() const { return mark[dev()].load(std::memory_order_acquire) == 0; }
+  void done() { mark[dev()].store(1, std::memory_order_release); }
+};
+
 }  // namespace tnb

@@ -242,10 +242,10 @@ static int launch_gemm(GemmArgs& g, int64_t batch, cudaStream_t st) {
   constexpr size_t ES = CPLX ? 16 : 8;
   constexpr size_t smem = (size_t)STAGES * (LA::ELEMS + LB::ELEMS) * ES;
   auto kern = gemm_kernel<CPLX, SMALL, A_KC, B_KC, VEC>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    once.done();
   }
   g.tiles_m = (int)((g.M + C_::BM - 1) / C_::BM);
   g.tiles_n = (int)((g.N + C_::BN - 1) / C_::BN);

@@ -2,6 +2,7 @@
 // Off by default; bench.py switches it on for ONE extra pass after the timed
 // steps to attribute device time to kernel classes and to compute the roofline
 // figures of the dominant kernel from live measurements.
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -11,6 +12,7 @@ namespace tnb {
 bool g_prof_on = false;
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; double work; long long launches; };
+static std::mutex g_mu;  // the record / event pools are shared by every host thread driving the library
 static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_pool;
 static double g_ms[KC_COUNT], g_work[KC_COUNT];
@@ -25,6 +27,7 @@ static cudaEvent_t get_event() {
 
 ProfScope::ProfScope(int c, cudaStream_t s, double w) : cls(c), st(s), work(w), l0(g_launches.load()), idx(-1) {
   if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_mu);
   ProfRec r;
   r.cls = c; r.work = w; r.launches = 0;
   r.e0 = get_event(); r.e1 = get_event();
@@ -35,6 +38,8 @@ ProfScope::ProfScope(int c, cudaStream_t s, double w) : cls(c), st(s), work(w), 
 
 ProfScope::~ProfScope() {
   if (idx < 0) return;
+  std::lock_guard<std::mutex> lock(g_mu);
+  if ((size_t)idx >= g_recs.size()) return;  // profile was drained while this scope was open
   ProfRec& r = g_recs[(size_t)idx];
   r.launches = g_launches.load() - l0;
   r.work = work;
@@ -42,6 +47,7 @@ ProfScope::~ProfScope() {
 }
 
 static void drain() {
+  std::lock_guard<std::mutex> lock(g_mu);
   for (ProfRec& r : g_recs) {
     cudaEventSynchronize(r.e1);
     float ms = 0.f;

@@ -59,9 +59,14 @@ template <> __device__ __forceinline__ cplx warp_sum_t<cplx>(cplx v) {
   return make_double2(warp_sum(v.x), warp_sum(v.y));
 }
 
-// kernel experiments: phase timestamps of CTA 0 / thread 0 of the LAST panel launch (TNB_QR_FAST_PANEL=3)
+// kernel experiments (build with -DTNB_EXP_STAMPS -DTNB_EXP_QR_FAST_PANEL=3): phase timestamps of CTA 0 /
+// thread 0 of the LAST panel launch.  Release builds compile none of this.
+#ifdef TNB_EXP_STAMPS
 __device__ long long g_qr_dbg[32];
 #define QR_STAMP(k) do { if ((a.fast & 2) && crank == 0 && tid == 0) g_qr_dbg[k] = clock64(); } while (0)
+#else
+#define QR_STAMP(k) do { } while (0)
+#endif
 
 constexpr int QP = QR_NB + 4;  // pitch of the 32 x 32 matrices of the fast path (conflict-free DMMA fragments)
 
@@ -763,8 +768,20 @@ static inline unsigned blocks_for(int64_t n) {
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// kernel experiments: TNB_QR_FAST_PANEL=0 forces the column-by-column Householder panel
-static const int g_qr_fast_panel = getenv("TNB_QR_FAST_PANEL") ? atoi(getenv("TNB_QR_FAST_PANEL")) : 1;
+// Compile-time switches of the kernel experiments (scratch/): the release build has no run-time knobs.
+#ifndef TNB_EXP_QR_FAST_PANEL
+#define TNB_EXP_QR_FAST_PANEL 1   // 0: column-by-column Householder panel everywhere
+#endif
+#ifndef TNB_EXP_QR_OVERLAP
+#define TNB_EXP_QR_OVERLAP 1      // 0: everything on the caller's stream
+#endif
+#ifndef TNB_EXP_QR_SIDE_PCT
+#define TNB_EXP_QR_SIDE_PCT 20    // share of the split-K scratch given to the side stream
+#endif
+#ifndef TNB_EXP_QR_BCGS
+#define TNB_EXP_QR_BCGS 2         // 0: Householder path everywhere; 1: no lagged second pass
+#endif
+constexpr int g_qr_fast_panel = TNB_EXP_QR_FAST_PANEL;
 
 constexpr int QR_NBO = 128;  // outer block: trailing updates and the explicit Q use K = 128 GEMMs
 
@@ -820,15 +837,11 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
   a.rows_per = rows_per;
   a.pitch = pitch;
   auto kern = qr_panel_kernel<T>;
-  static size_t configured_smem = 0;
-  static bool nonportable = false;
-  if (smem > configured_smem) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    configured_smem = 220 * 1024;
-  }
-  if (C > 8 && !nonportable) {
     TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    nonportable = true;
+    once.done();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)C, 1, 1);
@@ -1015,8 +1028,7 @@ struct QrSide {
   }
 };
 static thread_local QrSide g_qr_side;
-// kernel experiments: TNB_QR_OVERLAP=0 keeps everything on the caller's stream
-static const int g_qr_overlap = getenv("TNB_QR_OVERLAP") ? atoi(getenv("TNB_QR_OVERLAP")) : 1;
+constexpr int g_qr_overlap = TNB_EXP_QR_OVERLAP;
 
 // G = I + E (n x n Hermitian, upper triangle read) with |E| <= tol entrywise  ->  R = I + U, Rinv = I - U,
 // U = striu(E) + diag(E)/2: the Cholesky factor and its inverse to O(|E|^2).  Any entry outside tol (or a
@@ -1073,7 +1085,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   // the last quarter of the split-K scratch, which also keeps its grid below one wave (an SM stays free for
   // the single-CTA Cholesky kernel)
   const bool overlap = lagged && g_qr_overlap && L.sk_bytes > 0;
-  static const int side_pct = getenv("TNB_QR_SIDE_PCT") ? atoi(getenv("TNB_QR_SIDE_PCT")) : 20;  // kernel experiments
+  constexpr int side_pct = TNB_EXP_QR_SIDE_PCT;
   const size_t sk_main = overlap ? ((L.sk_bytes / 100) * (100 - side_pct)) & ~(size_t)255 : L.sk_bytes;
   void* sk_side = overlap ? (void*)(base + L.off_sk + sk_main) : nullptr;
   const size_t sk_side_bytes = overlap ? L.sk_bytes - sk_main : 0;
@@ -1100,10 +1112,10 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   TNB_CUDA_CHECK(cudaMemsetAsync(Rg, 0, (size_t)k * n * sizeof(T), st));
   auto kern = chol_inv_kernel<T>;
   constexpr size_t ci_smem = (size_t)3 * CI_N * CI_P * sizeof(T);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ci_smem));
-    configured = true;
+    once.done();
   }
   // the small factor of a pass: G (ld ldg) -> Rout (ld ldr), R^-1 -> Rinv (ld LDB)
   struct Factor { int kind; T* Rout; int64_t ldr; double rel_floor, abs_floor, near_tol; };
@@ -1343,8 +1355,7 @@ static int qr_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, 
 }
 
 // internal entry used by svd.cu as well
-// kernel experiments: TNB_QR_BCGS=0 forces the Householder path everywhere
-static const int g_qr_bcgs = getenv("TNB_QR_BCGS") ? atoi(getenv("TNB_QR_BCGS")) : 2;
+constexpr int g_qr_bcgs = TNB_EXP_QR_BCGS;
 
 int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, void* R, void* ws, int scale_mode,
        double** scale_out, cudaStream_t st) {
@@ -1352,7 +1363,7 @@ int qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, voi
   const int64_t k = m < n ? m : n;
   if (g_qr_bcgs && R && k >= 2 * QR_CB) {
     int rc = 1;
-    // first the lagged second pass (TNB_QR_BCGS >= 2, the default), then two passes per block, then Householder
+    // first the lagged second pass, then two passes per block, then Householder
     for (int lag = (g_qr_bcgs >= 2 && k > 2 * QR_CB) ? 1 : 0; lag >= 0 && rc == 1; --lag) {
       rc = (dtype == TNB_F64) ? qr_bcgs2<double>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, lag != 0, st)
                               : qr_bcgs2<cplx>(dtype, m, n, A, lda, Q, R, ws, scale_mode, scale_out, lag != 0, st);
@@ -1381,9 +1392,11 @@ extern "C" int tnb_qr(int dtype, int64_t m, int64_t n, const void* A, int64_t ld
   return tnb::qr(dtype, m, n, A, lda, Q, R, ws, 1, nullptr, (cudaStream_t)stream);
 }
 
+#ifdef TNB_EXP_STAMPS
 // kernel experiments: phase timestamps (clock64) of the last fast-path panel, see QR_STAMP
 extern "C" int tnb_debug_qr_stamps(long long* out, int n) {
   if (!out || n <= 0 || n > 32) return TNB_E_ARG;
   TNB_CUDA_CHECK(cudaMemcpyFromSymbol(out, tnb::g_qr_dbg, (size_t)n * sizeof(long long)));
   return 0;
 }
+#endif

@@ -145,6 +145,13 @@ template <typename T> struct Rot { typename Num<T>::real_t c; T sp; };
 // under- or overflows whatever the size of the columns -- and the tests are made on the squared cosine
 // itself.  MUFU approximations (rcp, rsqrt) are good enough: the rotation the MATRIX sees is
 // re-normalised in double precision (load_rot), the Gram matrix only ever decides angles.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float2 sel(bool c, float2 a, float2 b) { return make_float2(c ? a.x : b.x, c ? a.y : b.y); }
+__device__ __forceinline__ float sel(bool c, float a, float b) { return c ? a : b; }
+__device__ __forceinline__ cplx sel(bool c, cplx a, cplx b) { return make_double2(c ? a.x : b.x, c ? a.y : b.y); }
+__device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
+
 template <typename T>
 __device__ __forceinline__ Rot<T> make_rot_vals(typename Num<T>::real_t alpha, typename Num<T>::real_t beta, T gam,
                                                 double tol2, unsigned& state) {
@@ -152,22 +159,22 @@ __device__ __forceinline__ Rot<T> make_rot_vals(typename Num<T>::real_t alpha, t
   Rot<T> r;
   r.c = 1; r.sp = N_::zero();
   if constexpr (sizeof(typename N_::real_t) == 4) {
-    if (alpha > 0.f && beta > 0.f) {
-      const float inv = __frcp_rn(fmaxf(alpha, beta));
-      const float a_ = alpha * inv, b_ = beta * inv;
-      const T g_ = N_::scale(gam, inv);
-      const float ag2 = N_::abs2(g_);
-      const float cos2 = __fdividef(ag2, a_ * b_);
-      if (cos2 > (float)tol2) {
-        state |= (cos2 > 1e-14f) ? 3u : 1u;
-        const float tau = 0.5f * (b_ - a_);
-        const float rh = rsqrtf(fmaf(tau, tau, ag2));
-        const float c2 = fmaf(0.5f * fabsf(tau), rh, 0.5f);
-        const float rc = rsqrtf(c2);
-        r.c = c2 * rc;
-        r.sp = N_::scale(g_, copysignf(0.5f * rh * rc, tau));
-      }
-    }
+    // branch-free (this is the head of the dependent chain of a step): garbage from a zero column or an
+    // already orthogonal pair (0 * inf, rsqrt(0)) is discarded by the final selects -- NaN compares false
+    const float inv = rcp_approx(fmaxf(alpha, beta));
+    const float a_ = alpha * inv, b_ = beta * inv;
+    const T g_ = N_::scale(gam, inv);
+    const float ag2 = N_::abs2(g_);
+    const float cos2 = ag2 * rcp_approx(a_ * b_);
+    const bool rot = alpha > 0.f && beta > 0.f && cos2 > (float)tol2;
+    const float tau = 0.5f * (b_ - a_);
+    const float rh = rsqrt_approx(fmaf(tau, tau, ag2));
+    const float c2 = fmaf(0.5f * fabsf(tau), rh, 0.5f);
+    const float rc = rsqrt_approx(c2);
+    const T sp = N_::scale(g_, copysignf(0.5f * rh * rc, tau));
+    r.c = rot ? c2 * rc : 1.f;
+    r.sp = sel(rot, sp, N_::zero());
+    state |= rot ? ((cos2 > 1e-14f) ? 3u : 1u) : 0u;
   } else {
     const double ag2 = N_::abs2(gam);
     const double ab = alpha * beta;
@@ -222,15 +229,18 @@ __device__ __forceinline__ float2 rot_mix(float c, float2 x, float2 s, float2 y)
 
 // Entry (r, k) of B' = J_a^H B J_b for the 2 x 2 block B = [[b00, b01], [b10, b11]]
 // (J = [[c, sp], [-conj(sp), c]]); the same operation order as the full block update of the round kernel.
+// r and k differ from lane to lane: written with selects, not branches.
 template <typename T>
 __device__ __forceinline__ T rotated_entry(T b00, T b01, T b10, T b11, const Rot<T>& Ra, const Rot<T>& Rb, int r, int k) {
   typedef Num<T> N_;
-  const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));
-  T t0, t1;
-  if (k == 0) { t0 = rot_mix(Rb.c, b00, msb, b01); t1 = rot_mix(Rb.c, b10, msb, b11); }
-  else { t0 = rot_mix(Rb.c, b01, Rb.sp, b00); t1 = rot_mix(Rb.c, b11, Rb.sp, b10); }
-  if (r == 0) return rot_mix(Ra.c, t0, N_::sub(N_::zero(), Ra.sp), t1);
-  return rot_mix(Ra.c, t1, N_::conj(Ra.sp), t0);
+  const bool k1 = (k != 0), r1 = (r != 0);
+  // column k of T1 = B J_b:  T1[:,0] = c B[:,0] - conj(sp) B[:,1],  T1[:,1] = c B[:,1] + sp B[:,0]
+  const T sb = sel(k1, Rb.sp, N_::sub(N_::zero(), N_::conj(Rb.sp)));
+  const T t0 = rot_mix(Rb.c, sel(k1, b01, b00), sb, sel(k1, b00, b01));
+  const T t1 = rot_mix(Rb.c, sel(k1, b11, b10), sb, sel(k1, b10, b11));
+  // row r of J_a^H T1,  J_a^H = [[c, -sp], [conj(sp), c]]
+  const T sa = sel(r1, N_::conj(Ra.sp), N_::sub(N_::zero(), Ra.sp));
+  return rot_mix(Ra.c, sel(r1, t1, t0), sa, sel(r1, t0, t1));
 }
 
 // ---- rotation phase of a round: parallel-ordered Jacobi rotations on G, accumulated in W ---------------------
@@ -243,15 +253,16 @@ __device__ __forceinline__ T rotated_entry(T b00, T b01, T b10, T b11, const Rot
 //   G' = J^H G J is Hermitian: warps 0, 4, 1, 5, 2 own the 136 blocks ta <= tb (thread = one 2 x 2 block,
 //     B' = J_a^H B J_b) and store the mirror image too (G's pitch of 33 makes column stores conflict-free);
 //   W' = W J acts on rows independently: with S = 2, 4 or 8 CTAs in the cluster each CTA only carries
-//     32 / S rows of W through the steps (thread = rows 2wa, 2wa+1 x columns of pair wb); the last step
-//     writes its rows into every CTA of the cluster (distributed shared memory), one cluster barrier follows.
+//     32 / S rows of W through the steps (task = one row x the two columns of pair wb, dealt to up to ten
+//     warps spread over the four sub-partitions); the last step writes its rows into every CTA of the
+//     cluster (distributed shared memory), one cluster barrier follows.
 // G and W ping-pong between two buffers, the rotations between rc/rsp[0] and [1].
 // GT is the precision of the Gram domain (T itself, or its single-precision counterpart: see the call site).
 struct RotCtx {
   const unsigned char (*rr)[JP / 2][2];
   const unsigned int (*nxt)[JP / 2];
   const unsigned char (*gt)[2];
-  int nsteps, S, crank, w_tasks, w_first, g0, w0;
+  int nsteps, S, crank, w_tasks, w_first, g0, wi, nw;
   bool wsplit;
   double tol2;
 };
@@ -270,6 +281,11 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
     s_rc[0][lane] = r.c;
     s_rsp[0][lane] = r.sp;
   }
+  // the rotation warp fetches its table word one step ahead (it does not depend on the data)
+  unsigned nx_ahead = (warp == ROTW && lane < JP / 2 && nsteps > 1) ? cx.nxt[0][lane] : 0u;
+  // a G task keeps its block (ta, tb) through all steps
+  int g_ta = 0, g_tb = 0;
+  if (cx.g0 >= 0 && cx.g0 + lane < NGB) { g_ta = cx.gt[cx.g0 + lane][0]; g_tb = cx.gt[cx.g0 + lane][1]; }
   __syncthreads();
   JSTAMP(0, threadIdx.x == 0);
   for (int step = 0; step < nsteps; ++step) {
@@ -281,10 +297,10 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
     T* Wn = W + (cur ^ 1) * (JP * JGP);
     if (warp == ROTW) {
       if (lane < JP / 2 && step + 1 < nsteps) {
-        const unsigned nx_ = cx.nxt[step][lane];
-        const int a1 = nx_ & 0xff, r1 = (nx_ >> 8) & 1, a2 = (nx_ >> 16) & 0xff, r2 = (nx_ >> 24) & 1;
-        const int p1 = cx.rr[step][a1][0], q1 = cx.rr[step][a1][1];
-        const int p2 = cx.rr[step][a2][0], q2 = cx.rr[step][a2][1];
+        const unsigned nx_ = nx_ahead;
+        if (step + 2 < nsteps) nx_ahead = cx.nxt[step + 1][lane];
+        const int p1 = nx_ & 31, q1 = (nx_ >> 5) & 31, p2 = (nx_ >> 10) & 31, q2 = (nx_ >> 15) & 31;
+        const int a1 = (nx_ >> 20) & 15, a2 = (nx_ >> 24) & 15, r1 = (nx_ >> 28) & 1, r2 = (nx_ >> 29) & 1;
         Rot<GT> R1, R2;
         R1.c = s_rc[cur][a1]; R1.sp = s_rsp[cur][a1];
         R2.c = s_rc[cur][a2]; R2.sp = s_rsp[cur][a2];
@@ -299,7 +315,7 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
     } else if (cx.g0 >= 0) {
       const int t = cx.g0 + lane;
       if (t < NGB) {
-        const int ta = cx.gt[t][0], tb = cx.gt[t][1];
+        const int ta = g_ta, tb = g_tb;
         const int pa = cx.rr[step][ta][0], qa = cx.rr[step][ta][1];
         const int pb = cx.rr[step][tb][0], qb = cx.rr[step][tb][1];
         Rot<GT> Ra, Rb;
@@ -326,34 +342,27 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
         Gn[pa * JGG + pb] = n00; Gn[pa * JGG + qb] = n01; Gn[qa * JGG + pb] = n10; Gn[qa * JGG + qb] = n11;
       }
       JSTAMP(3 + 4 * step, threadIdx.x == 0);
-    } else if (cx.w0 >= 0) {
-      const int task = cx.w0 + lane;
-      if (task < cx.w_tasks) {
-        const int wa = cx.w_first + (task >> 4), wb = task & 15;
+    } else if (cx.wi >= 0) {
+      for (int task = cx.wi * 32 + lane; task < cx.w_tasks; task += cx.nw * 32) {
+        const int row = cx.w_first + (task >> 4), wb = task & 15;
         const int pb = cx.rr[step][wb][0], qb = cx.rr[step][wb][1];
         const Rot<T> Rb = load_rot<T, GT>(s_rc[cur], s_rsp[cur], wb);
         const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));
-        const T w00 = Wc[(2 * wa) * JWP + pb], w01 = Wc[(2 * wa) * JWP + qb];
-        const T w10 = Wc[(2 * wa + 1) * JWP + pb], w11 = Wc[(2 * wa + 1) * JWP + qb];
-        const T v00 = rot_mix(Rb.c, w00, msb, w01), v01 = rot_mix(Rb.c, w01, Rb.sp, w00);
-        const T v10 = rot_mix(Rb.c, w10, msb, w11), v11 = rot_mix(Rb.c, w11, Rb.sp, w10);
-        Wn[(2 * wa) * JWP + pb] = v00;
-        Wn[(2 * wa) * JWP + qb] = v01;
-        Wn[(2 * wa + 1) * JWP + pb] = v10;
-        Wn[(2 * wa + 1) * JWP + qb] = v11;
+        const T w0 = Wc[row * JWP + pb], w1 = Wc[row * JWP + qb];
+        const T v0 = rot_mix(Rb.c, w0, msb, w1), v1 = rot_mix(Rb.c, w1, Rb.sp, w0);
+        Wn[row * JWP + pb] = v0;
+        Wn[row * JWP + qb] = v1;
         if (cx.wsplit && step == nsteps - 1) {
           // last step: the final rows also go to the other CTAs of the cluster (they never touch these rows)
           for (int q = 0; q < cx.S; ++q) {
             if (q == cx.crank) continue;
             T* Wr = cluster.map_shared_rank(Wn, q);
-            Wr[(2 * wa) * JWP + pb] = v00;
-            Wr[(2 * wa) * JWP + qb] = v01;
-            Wr[(2 * wa + 1) * JWP + pb] = v10;
-            Wr[(2 * wa + 1) * JWP + qb] = v11;
+            Wr[row * JWP + pb] = v0;
+            Wr[row * JWP + qb] = v1;
           }
         }
       }
-      JSTAMP(4 + 4 * step, lane == 0 && cx.w0 == 0);
+      JSTAMP(4 + 4 * step, lane == 0 && cx.wi == 0);
     }
     __syncthreads();
   }
@@ -367,6 +376,7 @@ template <typename T>
 __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   typedef Num<T> N_;
   constexpr bool CPLX = (sizeof(T) == 16);
+  JSTAMP(70, threadIdx.x == 0);
   cg::cluster_group cluster = cg::this_cluster();
   const int S = a.S;
   const int crank = (int)cluster.block_rank();
@@ -390,8 +400,8 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   __shared__ unsigned char s_rr[JB][JP / 2][2];
   // s_pos[step][i] = 2 * (rotation pair holding panel column i in that step) + (1 if i is the larger one)
   __shared__ unsigned char s_pos[JB][JP];
-  // s_nxt[step][a]: for rotation pair a of step + 1, the two pairs of `step` its columns come from and
-  // on which side: byte 0 = pair of the smaller column, byte 1 = its side, byte 2 / 3 = same for the larger
+  // s_nxt[step][a]: for rotation pair a of step + 1, the two pairs of `step` its columns come from, their
+  // columns, and on which side of its pair each column sits (packed, see below)
   __shared__ unsigned int s_nxt[JB][JP / 2];
   // s_gt[t] = (ta, tb), ta <= tb: the 136 blocks of the upper block triangle of G (16 x 16 blocks of 2 x 2)
   __shared__ unsigned char s_gt[JB * (JB + 1) / 2][2];
@@ -424,14 +434,20 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   if (tid < (nsteps - 1) * (JP / 2)) {
     const int st_ = tid / (JP / 2), pr_ = tid % (JP / 2);
     const unsigned p1 = s_pos[st_][s_rr[st_ + 1][pr_][0]], p2 = s_pos[st_][s_rr[st_ + 1][pr_][1]];
-    s_nxt[st_][pr_] = (p1 >> 1) | ((p1 & 1u) << 8) | ((p2 >> 1) << 16) | ((p2 & 1u) << 24);
+    // packed: columns (p1, q1) / (p2, q2) of the two source pairs (5 bits each), the pairs themselves (4 bits
+    // each) and the sides (1 bit each) -- one shared-memory word per rotation and step
+    const unsigned a1 = p1 >> 1, a2 = p2 >> 1;
+    s_nxt[st_][pr_] = (unsigned)s_rr[st_][a1][0] | ((unsigned)s_rr[st_][a1][1] << 5) | ((unsigned)s_rr[st_][a2][0] << 10) |
+                      ((unsigned)s_rr[st_][a2][1] << 15) | (a1 << 20) | (a2 << 24) | ((p1 & 1u) << 28) | ((p2 & 1u) << 29);
   }
   // Programmatic dependent launch: everything above (index tables, barrier set-up) ran while the previous
   // round was still finishing; from here on this grid reads what that round wrote.  The next launch in the
   // stream may be scheduled as soon as every CTA of this grid got here (its CTAs take over the SMs one by
   // one as ours exit, and wait at this same point).
+  JSTAMP(71, threadIdx.x == 0);
   griddep_wait();
   griddep_launch_dependents();
+  JSTAMP(72, threadIdx.x == 0);
   JacobiFlags* const flags = a.flags + blockIdx.y;   // one matrix of the batch per grid row
   if (flags->converged) return;  // uniform over all clusters of this matrix
   T* Xg = reinterpret_cast<T*>(a.X) + (int64_t)blockIdx.y * a.xstride;
@@ -528,6 +544,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     gram_units(accA, gmA, gnA, sA0 * SL, nA * SL);
     if (nB > 0) gram_units(accB, gmB, gnB, 0, nB * SL);
   }
+  JSTAMP(73, threadIdx.x == 0);
   // per-warp partial tiles -> slots (in the space of G), summed per tile in a fixed order -> Gpart
   T* slots = G;  // [16 warps][2][64]
   {
@@ -577,6 +594,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     }
   }
   cluster.sync();  // all remote reads done before any CTA overwrites its partials (or exits)
+  JSTAMP(74, threadIdx.x == 0);
   for (int idx = tid; idx < JP * JP; idx += JT) {
     const int i = idx / JP, j = idx - i * JP;
     W[i * JWP + j] = (i == j) ? N_::one() : N_::zero();
@@ -596,17 +614,18 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   cx.rr = s_rr; cx.nxt = s_nxt; cx.gt = s_gt;
   cx.nsteps = nsteps; cx.S = S; cx.crank = crank;
   cx.wsplit = (S > 1) && (JP % S == 0) && (S <= JP / 2);
-  const int w_rowpairs = cx.wsplit ? (JP / 2) / S : JP / 2;   // row pairs of W carried by this CTA
-  cx.w_first = cx.wsplit ? crank * w_rowpairs : 0;
-  cx.w_tasks = w_rowpairs * (JP / 2);
-  cx.g0 = -1; cx.w0 = -1;
+  const int w_rows = cx.wsplit ? JP / S : JP;   // rows of W carried by this CTA
+  cx.w_first = cx.wsplit ? crank * w_rows : 0;
+  cx.w_tasks = w_rows * (JP / 2);
+  cx.nw = (cx.w_tasks + 31) / 32 < 10 ? (cx.w_tasks + 31) / 32 : 10;
+  cx.g0 = -1; cx.wi = -1;
   {
     const int g_warp[5] = {0, 4, 1, 5, 2};
-    const int w_warp[8] = {6, 10, 14, 3, 8, 9, 7, 12};
+    const int w_warp[10] = {8, 9, 10, 3, 12, 13, 6, 7, 14, 11};   // sub-partitions 0 1 2 3 0 1 2 3 2 3
 #pragma unroll
     for (int i = 0; i < 5; ++i) if (warp == g_warp[i]) cx.g0 = 32 * i;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) if (warp == w_warp[i] && 32 * i < cx.w_tasks) cx.w0 = 32 * i;
+    for (int i = 0; i < 10; ++i) if (warp == w_warp[i] && i < cx.nw) cx.wi = i;
   }
   cx.tol2 = a.tol * a.tol;
   unsigned state = 0;
@@ -643,6 +662,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   }
   W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
 #endif
+  JSTAMP(75, threadIdx.x == 0);
   if (crank == 0) {
     state = __reduce_or_sync(0xffffffffu, state);
     if (lane == 0 && state) atomicOr(&flags->state, state);
@@ -739,6 +759,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     }
   };
   if (resident >= 0) apply_chunk(resident);
+  JSTAMP(76, threadIdx.x == 0);
   for (int gch = crank; gch < a.nx + a.nv; gch += S) {
     if (gch == resident) continue;
     __syncthreads();
