@@ -107,6 +107,14 @@ class _RefBackend:
     def tensor(self, data, labels):
         return self.tn.Tensor(data, labels)
 
+    def mps_labelled(self, sites):
+        return self.od.MatrixProductState([self.tn.Tensor(a, l) for a, l in sites])
+
+    def overlap_norm_compress(self, a, b, chi):
+        self.od.inner_product_mps(a, b)          # onedim_core.py:1666
+        a.norm()                                 # :642
+        a.svd_compress(chi=chi)                  # :463
+
 
 class _PortBackend:
     def __init__(self, o):
@@ -149,6 +157,31 @@ class _PortBackend:
 
     def tensor(self, data, labels):
         return self.o.OT(data, labels)
+
+    def mps_labelled(self, sites):
+        o = self.o
+        return o.Chain([o.OT(a, l) for a, l in sites], "left", "right", "phys")
+
+    def overlap_norm_compress(self, a, b, chi):
+        o = self.o
+        o.inner_product_mps(a, b)
+        o.chain_norm(a)
+        o.svd_compress(a, chi=chi)
+
+
+def network_seconds(host_a, host_b, chi_keep, reps=1):
+    """The cfg 4 unit of work for ONE network on the CPU: <a|b>, |a|, a.svd_compress(chi).  host_a / host_b: lists
+    of (ndarray, labels) as tncontract_b200.batch.random_mps(..., on_host=True) returns.  -> (kind, [seconds])"""
+    use_all_host_threads()
+    kind, be = load_backend()
+    times = []
+    for _ in range(reps):
+        a = be.mps_labelled(host_a)
+        b = be.mps_labelled(host_b)
+        t0 = time.perf_counter()
+        be.overlap_norm_compress(a, b, chi_keep)
+        times.append(time.perf_counter() - t0)
+    return kind, times
 
 
 def full_sweep_seconds(host_sites, ws, wl, chi, max_steps, budget_s):

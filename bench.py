@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--d", type=int, default=2)
     ap.add_argument("--chi", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the batched (cfg 4) sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -337,6 +338,12 @@ def main():
         prof[name] = {"ms": pms.value, "work": pw.value, "launches": pl.value}
     lib.tnb_profile_enable(0)
 
+    # ---- batched path (cfg 4) sub-record: networks/s at this N, sharded over the ranks ---------------------
+    batched_rec = None
+    if not args.no_batched:
+        import bench_batch
+        batched_rec = bench_batch.measure(rank, world, networks_per_gpu=148, batch_size=148)
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -404,6 +411,18 @@ def main():
                    "norm_rel_err_vs_pinned": (abs(phi_norm - pin) / pin) if pin else None,
                    "pinned_by": "tests/golden/fullsize_cfg3.npz (unmodified reference, same inputs)" if pin else None},
     }
+    if batched_rec is not None:
+        line["batched"] = {k: batched_rec[k] for k in ("metric", "value", "unit", "n_gpus", "networks", "networks_per_gpu",
+                                                       "batch", "ms", "scaling", "launches_per_network_rank0",
+                                                       "ragged_group_fallbacks_rank0", "max_bond_after")}
+        if not args.no_cpu_baseline and world == 1:
+            from tncontract_b200 import batch as _b
+            ra = _ref_arm()
+            ha = _b.random_mps(3, 0, 0, 64, 4, 128, on_host=True)
+            hb = _b.random_mps(3, 0, 1, 64, 4, 128, on_host=True)
+            kind, tt = ra.network_seconds(ha, hb, 64, reps=2)
+            line["batched"]["cpu_baseline"] = {"value": 1.0 / tt[-1], "unit": "networks/s", "cores": ra.host_threads(),
+                                               "kind": kind, "sample": "network 0 of seed 3, second of two runs"}
     if not args.no_cpu_baseline and world == 1:
         # bounded sample (about 10-20 s of CPU): the work of 8 bulk sites at the bulk shapes, through the
         # reference's own tensor functions; a sweep is 99 site steps of which the flop profile makes

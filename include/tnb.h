@@ -168,6 +168,30 @@ int tnb_svd_project(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
 int tnb_truncation_count(const double* s, int64_t n, int64_t chi, double threshold, int relative,
                          double* info_device, double* s_scaled, void* stream);
 
+/* ==== batched path (BASELINE.json config 4: many independent networks of one shape) ==================
+ * The reference runs one network per Python loop iteration (onedim_core.py:463-484 svd_compress,
+ * :1666-1683 inner_product_mps); here ONE launch serves the same site of every network of a shard.
+ * Matrix b of a batch lives at base + b * stride (elements); all matrices of a batch share one shape.
+ * tnb_gemm above is already strided-batched and serves the absorbs and the ladder contractions. */
+
+/* batch x tnb_svd_project (np.linalg.svd, tensor.py:915, as used at onedim_core.py:317-351):
+ * A[b]: m x n (lda) -> U[b]: m x k, S[b]: k doubles (descending), P[b] = U^H A = diag(S) Vh: k x n (may be
+ * NULL), k = min(m, n).  One-sided Jacobi directly on the columns of A (tall) or A^H (wide), no QR
+ * pre-reduction; grid row = matrix, every matrix has its own convergence flag; the stream is synchronised
+ * once per batch of queued sweeps.  sweeps_out: the largest sweep count of the batch. */
+size_t tnb_svd_project_batched_workspace(int dtype, int64_t m, int64_t n, int64_t batch);
+int tnb_svd_project_batched(int dtype, int64_t m, int64_t n, int64_t batch, const void* A, int64_t lda, int64_t strideA,
+                            void* U, int64_t strideU, double* S, int64_t strideS, void* P, int64_t strideP,
+                            void* ws, size_t ws_bytes, int* sweeps_out, void* stream);
+/* batch x tnb_truncation_count: info_device[2b] = kept, [2b+1] = s[b][0]; s_scaled (stride as s) optional */
+int tnb_truncation_count_batched(const double* s, int64_t n, int64_t stride, int64_t batch, int64_t chi,
+                                 double threshold, int relative, double* info_device, double* s_scaled, void* stream);
+/* out_device[b] = Frobenius norm of the `per` contiguous elements at x + b * stride (np.linalg.norm,
+ * onedim_core.py:656-658 norm(canonical_form=...)) */
+int tnb_norm2_batched(int dtype, const void* x, int64_t per, int64_t stride, int64_t batch, double* out_device, void* stream);
+/* batch x tnb_fill_uniform: matrix b (per contiguous doubles) is filled from stream keys_device[b] */
+int tnb_fill_uniform_batched(double* out, int64_t per, int64_t batch, const unsigned long long* keys_device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,13 @@ SIGNATURES = {
     "tnb_svd": (_c.c_int, [_c.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _pi32, _vp]),
     "tnb_svd_project": (_c.c_int, [_c.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _pi32, _vp]),
     "tnb_truncation_count": (_c.c_int, [_vp, _i64, _i64, _dbl, _c.c_int, _vp, _vp, _vp]),
+    # batched path
+    "tnb_svd_project_batched_workspace": (_sz, [_c.c_int, _i64, _i64, _i64]),
+    "tnb_svd_project_batched": (_c.c_int, [_c.c_int, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                                           _vp, _sz, _pi32, _vp]),
+    "tnb_truncation_count_batched": (_c.c_int, [_vp, _i64, _i64, _i64, _i64, _dbl, _c.c_int, _vp, _vp, _vp]),
+    "tnb_norm2_batched": (_c.c_int, [_c.c_int, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "tnb_fill_uniform_batched": (_c.c_int, [_vp, _i64, _i64, _vp, _vp]),
 }
 
 _lib = None

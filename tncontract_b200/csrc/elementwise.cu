@@ -373,3 +373,122 @@ extern "C" int tnb_fill_uniform(double* out, int64_t n, unsigned long long key, 
   TNB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- batched helpers of the batched path (one launch for the same site of every network of a shard) --------
+namespace tnb {
+// matrix b: out[b * per + i] = U[0,1) from stream keys[b]
+__global__ void fill_uniform_batched_kernel(double* out, int64_t per, const unsigned long long* keys) {
+  const unsigned long long key = keys[blockIdx.y];
+  double* o = out + (int64_t)blockIdx.y * per;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += step) {
+    unsigned long long z = key + (unsigned long long)i * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    o[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  }
+}
+
+// kept-rank rule for matrix blockIdx.x (truncation_count_kernel with strides)
+__global__ void truncation_count_batched_kernel(const double* s, int64_t n, int64_t s_stride, int64_t chi, double threshold,
+                                                int relative, double* info, double* s_scaled) {
+  const int64_t b = blockIdx.x;
+  s += b * s_stride;
+  if (s_scaled) s_scaled += b * s_stride;
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const double s0 = n > 0 ? s[0] : 0.0;
+  const double bar = relative ? threshold * s0 : threshold;
+  const int64_t lim = (chi > 0 && chi < n) ? chi : n;
+  int local = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = s[i];
+    const bool above = (relative == 2) ? (v / s0 > threshold) : (v > bar);
+    if (i < lim && above) local++;
+    if (s_scaled) s_scaled[i] = v / s0;
+  }
+  atomicAdd(&cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0) { info[2 * b] = (double)cnt; info[2 * b + 1] = s0; }
+}
+
+// out[b] = |x[b]|_F of `per` contiguous elements, one CTA per matrix (amax-scaled: no overflow)
+template <typename T>
+__global__ void __launch_bounds__(512) norm2_batched_kernel(const T* x, int64_t per, int64_t stride, double* out) {
+  const T* xb = x + (int64_t)blockIdx.x * stride;
+  __shared__ double red[16];
+  __shared__ double bc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double mx = 0.0;
+  for (int64_t i = tid; i < per; i += 512) {
+    const double a = sqrt(Num<T>::abs2(xb[i]));
+    mx = (a != a) ? a : fmax(mx, a);
+    if (a != a) break;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = (mx != mx) ? mx : ((other != other) ? other : fmax(mx, other));
+  }
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    double m_ = 0.0;
+    for (int w = 0; w < 16; ++w) m_ = (m_ != m_) ? m_ : ((red[w] != red[w]) ? red[w] : fmax(m_, red[w]));
+    bc = m_;
+  }
+  __syncthreads();
+  const double amax = bc;
+  if (!(amax > 0.0) || !isfinite(amax)) { if (tid == 0) out[blockIdx.x] = amax; return; }
+  const double ia = 1.0 / amax;
+  double acc = 0.0;
+  for (int64_t i = tid; i < per; i += 512) acc += Num<T>::abs2(Num<T>::scale(xb[i], ia));
+  acc = warp_sum(acc);
+  __syncthreads();
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 16; ++w) t += red[w];
+    out[blockIdx.x] = amax * sqrt(t);
+  }
+}
+}  // namespace tnb
+
+extern "C" int tnb_fill_uniform_batched(double* out, int64_t per, int64_t batch, const unsigned long long* keys_device,
+                                        void* stream) {
+  if (!out || !keys_device || per < 0 || batch < 0 || batch > 65535) return TNB_E_ARG;
+  if (per == 0 || batch == 0) return 0;
+  unsigned gx = grid_for(per);
+  if (gx > 256) gx = 256;
+  tnb::fill_uniform_batched_kernel<<<dim3(gx, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(out, per, keys_device);
+  TNB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tnb_truncation_count_batched(const double* s, int64_t n, int64_t stride, int64_t batch, int64_t chi,
+                                            double threshold, int relative, double* info_device, double* s_scaled,
+                                            void* stream) {
+  if (!s || !info_device || n < 0 || batch < 0 || stride < n) return TNB_E_ARG;
+  if (batch == 0) return 0;
+  tnb::truncation_count_batched_kernel<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>(s, n, stride, chi, threshold,
+                                                                                        relative, info_device, s_scaled);
+  TNB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tnb_norm2_batched(int dtype, const void* x, int64_t per, int64_t stride, int64_t batch, double* out_device,
+                                 void* stream) {
+  if (!x || !out_device || per < 0 || batch < 0 || stride < per) return TNB_E_ARG;
+  if (batch == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (per == 0) { TNB_CUDA_CHECK(cudaMemsetAsync(out_device, 0, sizeof(double) * (size_t)batch, st)); return 0; }
+  ProfScope prof(KC_ELEMWISE, st, (double)per * (double)batch * (double)elem_size(dtype));
+  if (dtype == TNB_F64) tnb::norm2_batched_kernel<double><<<(unsigned)batch, 512, 0, st>>>((const double*)x, per, stride, out_device);
+  else if (dtype == TNB_C128) tnb::norm2_batched_kernel<double2><<<(unsigned)batch, 512, 0, st>>>((const double2*)x, per, stride, out_device);
+  else return TNB_E_ARG;
+  TNB_LAUNCH_CHECK();
+  return 0;
+}

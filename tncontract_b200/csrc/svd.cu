@@ -1031,6 +1031,14 @@ static JacobiPlan jacobi_plan(int64_t n, int64_t L, bool with_v, int batch) {
     const int cost = per * ch;  // elements of a row each CTA walks through
     if (cost < best) { best = cost; S = c; CH = ch; }
   }
+  // A batch that cannot be resident at one CTA per SM: shorter chunks bring the shared memory of a CTA under
+  // half an SM's, so that two CTAs (of different matrices) share an SM and one's rotation phase overlaps the
+  // other's tensor-core phases.  Costs a second pass over the chunks that are not resident (L2 traffic only).
+#ifndef TNB_EXP_NO_BATCH_HALVING
+  if (batch > 1 && S == 1 && (int64_t)p.npairs * batch > (int64_t)sm_count()) {
+    while (CH > 64 && smem_for(CH) > 110 * 1024) CH /= 2;
+  }
+#endif
   p.S = S; p.CH = CH;
   p.nx = (int)((L + CH - 1) / CH);
   p.nv = with_v ? (int)((n + CH - 1) / CH) : 0;
@@ -1234,6 +1242,205 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   return 0;
 }
 
+// ================================================================================================
+// Batched projection SVD: `batch` matrices of ONE shape in one set of launches (the batched path of
+// BASELINE.json config 4: the same site of every network of a shard).  No QR pre-reduction -- at these
+// sizes (a few hundred rows, chi ~ 128 columns) the whole matrix of a block pair fits the shared memory
+// of one CTA, and the grid row (blockIdx.y) of the round kernel is the matrix index, so one launch per
+// round serves the whole batch.  One-sided Jacobi runs directly on the columns of A (tall) or of A^H
+// (wide); every matrix carries its own convergence flag.
+//   tall (m >= n):  X = A      ->  Y = X V:  U = Y / sigma (sorted),  P = U^H A  (one batched GEMM)
+//   wide (m <  n):  X = A^H    ->  Y = X V:  U = V (accumulated),     P = Y^H    (sorted rows)
+// ================================================================================================
+
+// One CTA per matrix: x /= |x|_F (computed as amax * |x / amax|_F: no overflow), nrm[b] = |x|_F.
+// A zero matrix is left alone (nrm = 1); a non-finite one raises flags[b].bad.
+template <typename T>
+__global__ void __launch_bounds__(512) batched_unit_scale_kernel(T* x, int64_t per, double* nrm, JacobiFlags* flags) {
+  T* xb = x + (int64_t)blockIdx.x * per;
+  __shared__ double red[16];
+  __shared__ double bc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double mx = 0.0;
+  bool nan = false;
+  for (int64_t i = tid; i < per; i += 512) {
+    const double a = abs_t<T>(xb[i]);
+    if (!(a <= 1.79e308)) nan = true;   // NaN or Inf
+    mx = fmax(mx, a);
+  }
+  if (nan) mx = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = (mx != mx || other != other) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(mx, other);
+  }
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    double m_ = 0.0;
+    for (int w = 0; w < 16; ++w) m_ = (m_ != m_ || red[w] != red[w]) ? red[w] + m_ : fmax(m_, red[w]);
+    bc = m_;
+  }
+  __syncthreads();
+  const double amax = bc;
+  if (!(amax > 0.0) || !isfinite(amax)) {
+    if (tid == 0) {
+      nrm[blockIdx.x] = (amax == 0.0) ? 1.0 : amax;
+      if (amax != 0.0) flags[blockIdx.x].bad = 1;
+    }
+    return;
+  }
+  const double ia = 1.0 / amax;
+  double acc = 0.0;
+  for (int64_t i = tid; i < per; i += 512) acc += Num<T>::abs2(Num<T>::scale(xb[i], ia));
+  acc = warp_sum(acc);
+  __syncthreads();
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 16; ++w) t += red[w];
+    bc = sqrt(t);
+  }
+  __syncthreads();
+  const double rel = bc;                 // |x / amax|_F >= 1
+  const double inv = ia / rel;
+  for (int64_t i = tid; i < per; i += 512) xb[i] = Num<T>::scale(xb[i], inv);
+  if (tid == 0) {
+    const double v = amax * rel;
+    nrm[blockIdx.x] = v;
+    if (!isfinite(v)) flags[blockIdx.x].bad = 1;
+  }
+}
+
+template <typename T>
+__global__ void eye_rows_batched_kernel(T* V, int64_t n, int64_t total) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int64_t r = (i / n) % n, c = i % n;
+    V[i] = (r == c) ? Num<T>::one() : Num<T>::zero();
+  }
+}
+
+// rank_kernel for matrix blockIdx.y: sigma / perm advance by n, S by s_stride, scale and flags by one
+__global__ void __launch_bounds__(256) rank_batched_kernel(const double* sigma, int64_t n, int32_t* perm, double* S,
+                                                           int64_t s_stride, const double* scale, JacobiFlags* flags) {
+  const int64_t b = blockIdx.y;
+  sigma += b * n; perm += b * n; S += b * s_stride;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double raw = sigma[j];
+  const bool okj = isfinite(raw);
+  const double sj = okj ? raw : -1.0;
+  int64_t r = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double ri = sigma[i];
+    const double si = isfinite(ri) ? ri : -1.0;
+    r += (si > sj || (si == sj && i < j)) ? 1 : 0;
+  }
+  perm[r] = (int32_t)j;
+  const double sc = scale[b];
+  S[r] = raw * sc;
+  if (!okj || !isfinite(sc)) flags[b].bad = 1;
+}
+
+// gather_rows_kernel for matrix blockIdx.y (in / out advance by their strides, perm and S by n);
+// `mul` != null multiplies by mul[b] (undoes the unit-norm scaling)
+template <typename T>
+__global__ void gather_rows_batched_kernel(const T* in, int64_t ldi, int64_t in_stride, const int32_t* perm, const double* S,
+                                           T* out, int64_t ldo, int64_t out_stride, int64_t n, int64_t L, int conj, int scale,
+                                           int transpose, const double* mul) {
+  const int64_t b = blockIdx.y;
+  in += b * in_stride; out += b * out_stride; perm += b * n; S += b * n;
+  const double f = mul ? mul[b] : 1.0;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * L; i += step) {
+    int64_t k, c;
+    if (transpose) { c = i / n; k = i - c * n; } else { k = i / L; c = i - k * L; }
+    T v = in[(int64_t)perm[k] * ldi + c];
+    if (conj) v = Num<T>::conj(v);
+    double g = f;
+    if (scale) { const double s_ = S[perm[k]]; g = s_ > 0.0 ? f / s_ : 0.0; }
+    v = Num<T>::scale(v, g);
+    if (transpose) out[c * ldo + k] = v; else out[k * ldo + c] = v;
+  }
+}
+
+struct SvdBatchLayout { int64_t k, Lx; size_t off_x, off_v, off_sig, off_perm, off_flags, off_nrm, total; };
+static SvdBatchLayout svd_batch_layout(int dtype, int64_t m, int64_t n, int64_t batch) {
+  SvdBatchLayout L;
+  const size_t es = elem_size(dtype);
+  const bool wide = m < n;
+  L.k = wide ? m : n;
+  L.Lx = wide ? n : m;
+  size_t o = 0;
+  L.off_x = o;     o += align_up((size_t)batch * m * n * es);
+  L.off_v = o;     o += wide ? align_up((size_t)batch * L.k * L.k * es) : 0;
+  L.off_sig = o;   o += align_up((size_t)batch * L.k * sizeof(double));
+  L.off_perm = o;  o += align_up((size_t)batch * L.k * sizeof(int32_t));
+  L.off_flags = o; o += align_up((size_t)batch * sizeof(JacobiFlags));
+  L.off_nrm = o;   o += align_up((size_t)batch * sizeof(double));
+  L.total = o;
+  return L;
+}
+
+template <typename T>
+static int svd_project_batched_impl(int dtype, int64_t m, int64_t n, int64_t batch, const void* A, int64_t lda, int64_t sA,
+                                    void* U, int64_t sU, double* S, int64_t sS, void* P, int64_t sP, void* ws,
+                                    int* sweeps_out, cudaStream_t st) {
+  const SvdBatchLayout L = svd_batch_layout(dtype, m, n, batch);
+  char* base = (char*)ws;
+  const bool wide = m < n;
+  const int64_t k = L.k, Lx = L.Lx;
+  T* Xt = (T*)(base + L.off_x);
+  T* Vt = wide ? (T*)(base + L.off_v) : nullptr;
+  double* sig = (double*)(base + L.off_sig);
+  int32_t* perm = (int32_t*)(base + L.off_perm);
+  JacobiFlags* flags = (JacobiFlags*)(base + L.off_flags);
+  double* nrm = (double*)(base + L.off_nrm);
+  int rc;
+  {  // Xt[b] = A[b]^T (tall: the columns of A become contiguous rows) or conj(A[b]) (wide: X = A^H)
+    const int64_t sh[3] = {batch, k, Lx};
+    const int64_t is_tall[3] = {sA, 1, lda}, is_wide[3] = {sA, lda, 1};
+    rc = permute_view(dtype, A, 3, sh, wide ? is_wide : is_tall, Xt, 1.0, 0.0, wide ? 1 : 0, st);
+    if (rc) return rc;
+  }
+  TNB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(JacobiFlags) * (size_t)batch, st));
+  batched_unit_scale_kernel<T><<<(unsigned)batch, 512, 0, st>>>(Xt, k * Lx, nrm, flags);
+  TNB_LAUNCH_CHECK();
+  if (wide) {
+    eye_rows_batched_kernel<T><<<blocks_for(batch * k * k), 256, 0, st>>>(Vt, k, batch * k * k);
+    TNB_LAUNCH_CHECK();
+  }
+  rc = jacobi<T>(Xt, Lx, Lx, k * Lx, Vt, k * k, k, (int)batch, flags, sweeps_out, st);
+  if (rc) return rc;
+  row_norm_kernel<T><<<(unsigned)((batch * k + 7) / 8), 256, 0, st>>>(Xt, Lx, batch * k, Lx, sig);
+  TNB_LAUNCH_CHECK();
+  rank_batched_kernel<<<dim3((unsigned)((k + 255) / 256), (unsigned)batch), 256, 0, st>>>(sig, k, perm, S, sS, nrm, flags);
+  TNB_LAUNCH_CHECK();
+  unsigned gx = blocks_for(k * Lx);
+  if (gx > 64) gx = 64;
+  if (!wide) {
+    gather_rows_batched_kernel<T><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(Xt, Lx, k * Lx, perm, sig, (T*)U, k, sU, k, Lx, 0,
+                                                                          1, 1, nullptr);
+    TNB_LAUNCH_CHECK();
+    if (P) {
+      rc = gemm(dtype, TNB_OP_C, TNB_OP_N, k, n, m, 1, 0, U, k, sU, A, lda, sA, 0, 0, P, n, sP, batch, st);
+      if (rc) return rc;
+    }
+  } else {
+    if (P) {
+      gather_rows_batched_kernel<T><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(Xt, Lx, k * Lx, perm, sig, (T*)P, n, sP, k, Lx,
+                                                                            1, 0, 0, nrm);
+      TNB_LAUNCH_CHECK();
+    }
+    gather_rows_batched_kernel<T><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(Vt, k, k * k, perm, sig, (T*)U, k, sU, k, k, 0, 0,
+                                                                          1, nullptr);
+    TNB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 }  // namespace tnb
 
 #ifdef TNB_EXP_STAMPS
@@ -1271,4 +1478,27 @@ extern "C" int tnb_svd_project(int dtype, int64_t m, int64_t n, const void* A, i
   if (ws_bytes < tnb::svd_layout(dtype, m, n).total) return TNB_E_WORKSPACE;
   if (dtype == TNB_F64) return tnb::svd_impl<double>(dtype, m, n, A, lda, U, S, P, ws, sweeps_out, 1, (cudaStream_t)stream);
   return tnb::svd_impl<tnb::cplx>(dtype, m, n, A, lda, U, S, P, ws, sweeps_out, 1, (cudaStream_t)stream);
+}
+
+extern "C" size_t tnb_svd_project_batched_workspace(int dtype, int64_t m, int64_t n, int64_t batch) {
+  if (m <= 0 || n <= 0 || batch <= 0 || (dtype != TNB_F64 && dtype != TNB_C128)) return 0;
+  return tnb::svd_batch_layout(dtype, m, n, batch).total;
+}
+
+extern "C" int tnb_svd_project_batched(int dtype, int64_t m, int64_t n, int64_t batch, const void* A, int64_t lda,
+                                       int64_t strideA, void* U, int64_t strideU, double* S, int64_t strideS, void* P,
+                                       int64_t strideP, void* ws, size_t ws_bytes, int* sweeps_out, void* stream) {
+  if (dtype != TNB_F64 && dtype != TNB_C128) return TNB_E_ARG;
+  if (m < 0 || n < 0 || batch < 0 || lda < n) return TNB_E_ARG;
+  if (sweeps_out) *sweeps_out = 0;
+  if (m == 0 || n == 0 || batch == 0) return 0;
+  if (batch > 65535) return TNB_E_UNSUPPORTED;
+  const int64_t k = m < n ? m : n;
+  if (!A || !S || !U || !ws || strideA < m * lda || strideU < m * k || strideS < k || (P && strideP < k * n)) return TNB_E_ARG;
+  if (ws_bytes < tnb::svd_batch_layout(dtype, m, n, batch).total) return TNB_E_WORKSPACE;
+  if (dtype == TNB_F64)
+    return tnb::svd_project_batched_impl<double>(dtype, m, n, batch, A, lda, strideA, U, strideU, S, strideS, P, strideP, ws,
+                                                 sweeps_out, (cudaStream_t)stream);
+  return tnb::svd_project_batched_impl<tnb::cplx>(dtype, m, n, batch, A, lda, strideA, U, strideU, S, strideS, P, strideP, ws,
+                                                  sweeps_out, (cudaStream_t)stream);
 }
