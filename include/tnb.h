@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TNB_MAX_RANK 12
+#define TNB_MAX_RANK 24
 
 enum { TNB_F64 = 0, TNB_C128 = 1 };
 

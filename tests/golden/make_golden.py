@@ -285,6 +285,10 @@ def gen_fixture():
     with open("/root/reference/tncontract/tests/random_10site_mps.dat", "rb") as f:
         psi = pickle.load(f, encoding="latin1")
     g.chain("psi", psi)
+    # the same object pickled again by the reference's classes under this Python (protocol 2): the interchange
+    # fixture of tests/test_persist.py (the original .dat stays in /root/reference)
+    with open(os.path.join(HERE, "ref_pickle_10site.dat"), "wb") as f:
+        pickle.dump(psi, f, protocol=2)
     g.scalar("norm", psi.norm())
     g.scalar("ip", od.inner_product_mps(psi, psi))
     a = psi.copy(); a.svd_compress(threshold=1e-12, normalise=False)

@@ -320,10 +320,11 @@ def test_peps_boundary_contraction(backend):
     assert net.can_contract()
     cols = net.mps_contract(chi, return_all_columns=True, tolerance=1e-14)
     for i, c in enumerate(cols[:-1]):
-        # site 0 carries the long-double norm (host array, like the reference); the double-layer
-        # network has exactly degenerate singular values, so only the state as a whole is compared
-        assert np.asarray(c[0].data).dtype == np.longdouble
-        c[0] = tn.Tensor(np.asarray(c[0].data).astype(np.float64), c[0].labels)
+        # `mps_copy[0].data *= norm` (square_lattice.py:177) multiplies a float64 array by the long-double
+        # accumulator IN PLACE: NumPy keeps float64, and so does the device array (it stays a working tensor).
+        # The double-layer network has exactly degenerate singular values, so only the state as a whole is compared
+        assert np.asarray(c[0].data).dtype == np.float64
+        assert isinstance(c[0].data, tn.DevArray)
         check_chain(c, g, "col.%d" % i, backend, values=False)
     val = net.mps_contract(chi, tolerance=1e-14)
     assert str(np.asarray(val.data).dtype) == g.meta["result_dtype"]

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TNB_LIB_PATH") or os.path.join(_HERE, "lib", "libtnb.so")  # override: kernel experiments
 
-MAX_RANK = 12
+MAX_RANK = 24
 F64, C128 = 0, 1
 OP_N, OP_T, OP_C, OP_J = 0, 1, 2, 3
 E_NOCONV = -4

@@ -194,8 +194,14 @@ class DevArray:
         return DevArray(self.copy().t.view(-1))
 
     # ---- kernels ---------------------------------------------------------------------
-    def _permute_copy(self, alpha=1.0, conj=False):
-        out = _empty(self.shape, self.dtype)
+    def _permute_copy(self, alpha=1.0, conj=False, out=None):
+        """Contiguous copy of this (strided) view through tnb_permute; ``out``: an existing CONTIGUOUS DevArray of
+        the same shape and dtype to write into (used to place a slab inside a larger buffer)."""
+        if out is not None:
+            assert out.shape == self.shape and out.dtype == self.dtype and out.t.is_contiguous()
+            out = out.t
+        else:
+            out = _empty(self.shape, self.dtype)
         if self.size == 0:
             return DevArray(out)
         perm = (ctypes.c_int32 * max(self.ndim, 1))(*range(self.ndim))
@@ -278,14 +284,24 @@ class DevArray:
             _lib.check(_lib.load().tnb_scale_inplace(ctypes.byref(d), a.real, a.imag, stream_ptr()))
         return self
 
+    @staticmethod
+    def _narrow_longdouble(other):
+        """``x.data *= norm`` with the float128 norm accumulator of twodim.mps_contract (square_lattice.py:162,177,
+        188): NumPy keeps the float64 array and rounds the factor; so do we (the array stays on the device)."""
+        if isinstance(other, (np.longdouble, np.clongdouble)):
+            return complex(other) if isinstance(other, np.clongdouble) else float(other)
+        if isinstance(other, np.ndarray) and other.size == 1 and other.dtype in (np.longdouble, np.clongdouble):
+            return complex(other.item()) if other.dtype == np.clongdouble else float(other.item())
+        return other
+
     def __imul__(self, other):
-        s = self._as_scalar(other)
+        s = self._as_scalar(self._narrow_longdouble(other))
         if s is None:
             return NotImplemented
         return self._inplace_scale(s)
 
     def __itruediv__(self, other):
-        s = self._as_scalar(other)
+        s = self._as_scalar(self._narrow_longdouble(other))
         if s is None:
             return NotImplemented
         return self._inplace_scale(1.0 / s)

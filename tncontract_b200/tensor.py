@@ -54,6 +54,14 @@ class Tensor():
         t.labels = labels
         return t
 
+    # ---- persistence: the reference pickles a Tensor as {"data": ndarray, "_labels": list} -----------------
+    def __getstate__(self):
+        return {"data": np.asarray(self.data), "_labels": list(self._labels)}
+
+    def __setstate__(self, state):
+        self.data = _to_device(state["data"])
+        self._labels = [l.decode() if isinstance(l, bytes) else l for l in state["_labels"]]
+
     # ---- printing / comparison (tensor.py:57-93) -------------------------------
     def __repr__(self):
         return "Tensor(data=%r, labels=%r)" % (np.asarray(self.data), self.labels)
@@ -242,16 +250,21 @@ class Tensor():
         a diagonal matrix is inverted on device, anything else is refused."""
         if self.rank != 2 or self.shape[0] != self.shape[1]:
             raise np.linalg.LinAlgError("Last 2 dimensions of the array must be square")
-        n = self.shape[0]
         d = dv.diag_extract(self.data)
         full = float(self.data.norm())
-        if not np.isclose(float(d.norm()), full, rtol=1e-13, atol=0.0):
-            raise NotImplementedError("Tensor.inv() on the device handles diagonal matrices only")
-        dr = d if d.dtype == np.float64 else None
-        if dr is None:
-            raise NotImplementedError("Tensor.inv() on the device handles real diagonal matrices only")
-        self.data = dv.diag_embed(dr, np.float64, mode=2)
-        del n
+        if d.dtype == np.float64 and np.isclose(float(d.norm()), full, rtol=1e-13, atol=0.0):
+            if not np.all(np.asarray(d) != 0.0):
+                raise np.linalg.LinAlgError("Singular matrix")    # as np.linalg.inv
+            self.data = dv.diag_embed(d, np.float64, mode=2)      # real diagonal: 1 / s on the device
+            return
+        # general square matrix: A^-1 = V diag(1/s) U^H from the device SVD (np.linalg.inv raises on an exactly
+        # singular matrix; so do we)
+        u, s, vh = dv.svd(self.data.contiguous())
+        if not float(np.asarray(s)[-1]) > 0.0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        uh = u.transpose([1, 0]).conjugate().contiguous()         # k x m
+        dv.diag_scale_rows(uh, s, mode=2)                          # rows scaled by 1 / s
+        self.data = dv.tensordot(vh, uh, [0], [0], conj_a=True)    # (Vh)^H (S^-1 U^H)
 
     def add_suffix_to_labels(self, suffix):
         self.labels = [l + suffix for l in self.labels]
@@ -287,15 +300,15 @@ class Tensor():
         ax = self.labels.index(label)
         shape = list(self.shape)
         shape[ax] += inc
-        out = DevArray.zeros(shape, self.data.dtype)
-        sl = [slice(None)] * self.rank
-        sl[ax] = slice(inc, None) if before else slice(0, self.shape[ax])
-        # dst view <- src via a unit GEMM-free path: out_view = 1*src + 0*out_view
-        view = out[tuple(sl)]
-        tmp = self.data._axpby(view, 1.0, 1.0)  # src + zeros, contiguous
-        import torch
-        view.t.copy_(tmp.t)  # strided device-to-device placement (memory plumbing)
-        self.data = out
+        # With the padded axis in front the old data is ONE contiguous slab of the new buffer: tnb_permute writes
+        # it there directly; the result is handed back as a (lazy) view with the axis in its place.
+        n = self.shape[ax]
+        front = [ax] + [i for i in range(self.rank) if i != ax]
+        out = DevArray.zeros([shape[ax]] + [shape[i] for i in front[1:]], self.data.dtype)
+        slab = out[inc:] if before else out[:n]
+        self.data.transpose(front)._permute_copy(out=slab)
+        back = [front.index(i) for i in range(self.rank)]
+        self.data = out.transpose(back)
 
     def contract(self, *args, **kwargs):
         t = contract(self, *args, **kwargs)
