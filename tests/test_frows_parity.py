@@ -16,11 +16,19 @@ def dense(chain):
     return t
 
 
-def check_dense(chain, g, key, backend, tolerance=None):
+def check_dense(chain, g, key, backend, tolerance=None, phase_free=False):
+    """phase_free: compare up to ONE global phase.  right_canonical_to_canonical drops the 1 x 1 unitary of its
+    last SVD (onedim_core.py:1866-1869 "S and V are just scalars"), so the global phase of everything derived from
+    the canonical form is whatever sign / phase convention the SVD routine has -- LAPACK's in the fixture."""
     data, labels = g.tensor(key)
     t = dense(chain)
     assert list(t.labels) == labels
-    assert rel_err(np.asarray(t.data), data) <= (tolerance or tol(backend))
+    ours = np.asarray(t.data)
+    if phase_free:
+        ov = np.vdot(data, ours)
+        assert abs(abs(ov) - np.linalg.norm(data) ** 2) <= (tolerance or tol(backend)) * np.linalg.norm(data) ** 2
+        ours = ours * (np.conj(ov) / abs(ov))
+    assert rel_err(ours, data) <= (tolerance or tol(backend))
 
 
 def test_mps_apply_gate(backend):
@@ -80,23 +88,23 @@ def test_canonical_gates(backend):
     assert [int(b) for b in can.bonddims()] == g.meta["can1.bonds"]
     e = can.expval(g1, 2, gate_outputs=["out"], gate_inputs=["in"])
     assert abs(complex(np.asarray(e.data)) - complex(g.scalar("can1.expval"))) <= tol(backend) * abs(g.scalar("can1.expval"))
-    check_dense(od.canonical_to_right_canonical(can), g, "can1.dense", backend)
+    check_dense(od.canonical_to_right_canonical(can), g, "can1.dense", backend, phase_free=True)
     can.apply_gate(g2, 3, gate_outputs=["o1", "o2"], gate_inputs=["i1", "i2"], chi=4)
     assert [int(b) for b in can.bonddims()] == g.meta["can2.bonds"]
     assert [list(t.labels) for t in can] == g.meta["can2.labels"]
-    check_dense(od.canonical_to_right_canonical(can), g, "can2.dense", backend)
+    check_dense(od.canonical_to_right_canonical(can), g, "can2.dense", backend, phase_free=True)
     e = can.expval(g2, 1, gate_outputs=["o1", "o2"], gate_inputs=["i1", "i2"])
     assert abs(complex(np.asarray(e.data)) - complex(g.scalar("can2.expval2"))) <= tol(backend) * abs(g.scalar("can2.expval2"))
     can.swap_gate(2)
     assert [int(b) for b in can.bonddims()] == g.meta["can3.bonds"]
-    check_dense(od.canonical_to_right_canonical(can), g, "can3.dense", backend)
+    check_dense(od.canonical_to_right_canonical(can), g, "can3.dense", backend, phase_free=True)
     can.compress_bond(3, chi=2)
     assert [int(b) for b in can.bonddims()] == g.meta["can4.bonds"]
-    check_dense(od.canonical_to_right_canonical(can), g, "can4.dense", backend)
+    check_dense(od.canonical_to_right_canonical(can), g, "can4.dense", backend, phase_free=True)
     check_tensor(can.ptrace(1, 2), g.tensor("can4.ptrace"), tol(backend))
     lcan = od.left_canonical_to_canonical(od.left_canonical_form_mps(to_chain(g, "psi"), normalise=True))
     assert [int(b) for b in lcan.bonddims()] == g.meta["lcan.bonds"]
-    check_dense(od.canonical_to_left_canonical(lcan), g, "lcan.dense", backend)
+    check_dense(od.canonical_to_left_canonical(lcan), g, "lcan.dense", backend, phase_free=True)
     # the generator's psi had been through expval() and ptrace() by then, which canonise IN PLACE (:741, :825):
     # replaying them checks that side effect too
     p2 = to_chain(g, "psi")

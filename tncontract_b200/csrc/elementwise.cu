@@ -288,7 +288,6 @@ extern "C" int tnb_diag_scale(int dtype, void* x, int64_t rows, int64_t cols, in
 extern "C" int tnb_trace(const tnb_tensor_t* x, int axis1, int axis2, void* out, void* stream) {
   if (!valid_tensor(x) || !out || axis1 == axis2 || axis1 < 0 || axis2 < 0 || axis1 >= x->rank || axis2 >= x->rank)
     return TNB_E_ARG;
-  if (x->shape[axis1] != x->shape[axis2]) return TNB_E_ARG;
   tnb_tensor_t rest = *x;
   rest.rank = 0;
   for (int i = 0; i < x->rank; ++i) {
@@ -300,7 +299,9 @@ extern "C" int tnb_trace(const tnb_tensor_t* x, int axis1, int axis2, void* out,
   ViewParams p = make_view(&rest);
   if (p.numel == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t n = x->shape[axis1], sd = x->stride[axis1] + x->stride[axis2];
+  // np.trace sums the main diagonal, of length min(n1, n2) when the two axes differ in size
+  const int64_t n = x->shape[axis1] < x->shape[axis2] ? x->shape[axis1] : x->shape[axis2];
+  const int64_t sd = x->stride[axis1] + x->stride[axis2];
   if (x->dtype == TNB_F64) trace_kernel<double><<<grid_for(p.numel), 256, 0, st>>>((const double*)x->ptr, p, n, sd, (double*)out);
   else trace_kernel<double2><<<grid_for(p.numel), 256, 0, st>>>((const double2*)x->ptr, p, n, sd, (double2*)out);
   TNB_LAUNCH_CHECK();

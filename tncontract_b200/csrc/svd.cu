@@ -463,31 +463,40 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   };
   // Full chunks whose rows are 16-byte aligned move by TMA bulk copies (one 1-D copy per panel row,
   // issued by the lanes of warp 0, completion on an mbarrier); anything else by plain loads.
-  __shared__ __align__(8) uint64_t s_bar;
+  // Each row moves as two copies (first and second half of the chunk) completing on two barriers, so the Gram
+  // matrix of the first half is formed while the second half is still in flight.
+  __shared__ __align__(8) uint64_t s_bar[2];
   uint32_t bar_phase = 0;
-  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
   auto bulk_ok = [&](const T* base, int64_t ld, int len) -> bool {
     return len == CH && (CPLX || ((ld & 1) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0));
   };
-  auto load_chunk = [&](int g) {
+  // returns true when the chunk is in flight as bulk copies (wait_half(0), wait_half(1) follow), false when it
+  // was loaded with plain loads (a __syncthreads() makes it visible)
+  auto load_chunk = [&](int g) -> bool {
     T* base; int64_t ld, c0; int len;
     chunk_geom(g, base, ld, c0, len);
     if (bulk_ok(base, ld, len)) {
       if (warp == 0) {
         const int64_t r = grow(lane);
         const unsigned valid = __ballot_sync(0xffffffffu, r >= 0);
-        if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(__popc(valid) * CH * sizeof(T)));
+        const uint32_t hb = (uint32_t)((CH / 2) * sizeof(T));
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&s_bar[0], (uint32_t)__popc(valid) * hb);
+          mbar_arrive_expect_tx(&s_bar[1], (uint32_t)__popc(valid) * hb);
+        }
         __syncwarp();
-        if (r >= 0) bulk_g2s(P + lane * pitch, base + r * ld + c0, (uint32_t)(CH * sizeof(T)), &s_bar);
+        if (r >= 0) {
+          bulk_g2s(P + lane * pitch, base + r * ld + c0, hb, &s_bar[0]);
+          bulk_g2s(P + lane * pitch + CH / 2, base + r * ld + c0 + CH / 2, hb, &s_bar[1]);
+        }
       } else {
         for (int i = 0; i < JP; ++i) {  // rows past the end of the matrix are zero columns
           if (grow(i) >= 0) continue;
           for (int c = tid - 32; c < CH; c += JT - 32) P[i * pitch + c] = N_::zero();
         }
       }
-      mbar_wait(&s_bar, bar_phase);
-      bar_phase ^= 1;
-      return;
+      return true;
     }
     for (int idx = tid; idx < JP * CH; idx += JT) {
       const int i = idx / CH, c = idx - i * CH;
@@ -496,7 +505,9 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
       if (r >= 0 && c < len) v = base[r * ld + c0 + c];
       P[i * pitch + c] = v;
     }
+    return false;
   };
+  auto wait_half = [&](int h) { mbar_wait(&s_bar[h], bar_phase); };
 
   // ---- partial Gram matrix of this CTA's Xt chunks on the FP64 tensor pipe (DMMA.8x8x4) ----------
   // G[p][q] = sum_c conj(P[p][c]) P[q][c] is Hermitian: only the 10 upper 8 x 8 tiles of the 4 x 4 tile
@@ -536,13 +547,19 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     }
   };
   int resident = -1;
+  // this warp's units by half of the chunk (slices 0-3 | 4-7); tile B always starts at slice 0 and nB <= 4
+  const int a_lo_end = (sA0 + nA < 4) ? sA0 + nA : 4;           // tile A, first half:  slices [sA0, a_lo_end)
+  const int a_hi_beg = (sA0 > 4) ? sA0 : 4;                     // tile A, second half: slices [a_hi_beg, sA0 + nA)
   for (int gch = crank; gch < a.nx; gch += S) {
     __syncthreads();
-    load_chunk(gch);
+    const bool bulk = load_chunk(gch);
     __syncthreads();
     resident = gch;
-    gram_units(accA, gmA, gnA, sA0 * SL, nA * SL);
+    if (bulk) wait_half(0);
+    if (sA0 < a_lo_end) gram_units(accA, gmA, gnA, sA0 * SL, (a_lo_end - sA0) * SL);
     if (nB > 0) gram_units(accB, gmB, gnB, 0, nB * SL);
+    if (bulk) { wait_half(1); bar_phase ^= 1; }
+    if (a_hi_beg < sA0 + nA) gram_units(accA, gmA, gnA, a_hi_beg * SL, (sA0 + nA - a_hi_beg) * SL);
   }
   JSTAMP(73, threadIdx.x == 0);
   // per-warp partial tiles -> slots (in the space of G), summed per tile in a fixed order -> Gpart
@@ -621,7 +638,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   cx.g0 = -1; cx.wi = -1;
   {
     const int g_warp[5] = {0, 4, 1, 5, 2};
-    const int w_warp[10] = {8, 9, 10, 3, 12, 13, 6, 7, 14, 11};   // sub-partitions 0 1 2 3 0 1 2 3 2 3
+    const int w_warp[10] = {8, 9, 10, 6, 12, 13, 14, 3, 7, 11};   // sub-partitions 0 1 2 2 0 1 2 3 3 3: the rotation warp (15, sub-partition 3) keeps its issue port to itself as long as possible
 #pragma unroll
     for (int i = 0; i < 5; ++i) if (warp == g_warp[i]) cx.g0 = 32 * i;
 #pragma unroll
@@ -675,86 +692,78 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   auto apply_chunk = [&](int gch) {
     T* base; int64_t ld, c0; int len;
     chunk_geom(gch, base, ld, c0, len);
-    for (int cw = warp * 16; cw < CH; cw += (JT / 32) * 16) {
-      if (cw >= len) break;
-      // complex: 3-multiplication form, P1 = wr pr, P2 = wi pi, P3 = (wr + wi)(pr + pi):
-      //   re = P1 - P2,  im = P3 - P1 - P2   (24 DMMAs per k-step instead of 32)
-      double acc[4][2][CPLX ? 6 : 2];
+    const bool bulk = bulk_ok(base, ld, len);
+    // The chunk is processed in two halves of CH / 2 columns; inside a half a warp takes blocks of 8 columns.
+    // With bulk stores the first half is on its way to global memory while the second is being computed.
+    for (int h = 0; h < 2; ++h) {
+      const int hbeg = h * (CH / 2), hend = hbeg + CH / 2;
+      for (int cw = hbeg + warp * 8; cw < hend; cw += (JT / 32) * 8) {
+        if (cw >= len) break;
+        // complex: 3-multiplication form, P1 = wr pr, P2 = wi pi, P3 = (wr + wi)(pr + pi):
+        //   re = P1 - P2,  im = P3 - P1 - P2   (12 DMMAs per k-step instead of 16)
+        double acc[4][CPLX ? 6 : 2];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int r = 0; r < (CPLX ? 6 : 2); ++r) acc[mt][nt][r] = 0.0;
+          for (int r = 0; r < (CPLX ? 6 : 2); ++r) acc[mt][r] = 0.0;
 #ifdef TNB_EXP_SKIP_APPLY
-      for (int k0 = 0; k0 < 4; k0 += 4) {
+        for (int k0 = 0; k0 < 4; k0 += 4) {
 #else
-#pragma unroll 1
-      for (int k0 = 0; k0 < JP; k0 += 4) {
+#pragma unroll 2
+        for (int k0 = 0; k0 < JP; k0 += 4) {
 #endif
-        T av[4], bv[2];
+          T av[4];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JWP + mt * 8 + gq];
+          for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JWP + mt * 8 + gq];
+          const T bv = P[(k0 + tq) * pitch + cw + gq];
+          if constexpr (CPLX) {
+            const double bs = bv.x + bv.y;
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) bv[nt] = P[(k0 + tq) * pitch + cw + nt * 8 + gq];
-        if constexpr (CPLX) {
-          double as[4], bs[2];
+            for (int mt = 0; mt < 4; ++mt) {
+              dmma884(acc[mt][0], acc[mt][1], av[mt].x, bv.x);
+              dmma884(acc[mt][2], acc[mt][3], av[mt].y, bv.y);
+              dmma884(acc[mt][4], acc[mt][5], av[mt].x + av[mt].y, bs);
+            }
+          } else {
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) as[mt] = av[mt].x + av[mt].y;
+            for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][0], acc[mt][1], av[mt], bv);
+          }
+        }
+        __syncwarp();
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) bs[nt] = bv[nt].x + bv[nt].y;
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt].x, bv[nt].x);
-              dmma884(acc[mt][nt][2], acc[mt][nt][3], av[mt].y, bv[nt].y);
-              dmma884(acc[mt][nt][4], acc[mt][nt][5], as[mt], bs[nt]);
+        for (int mt = 0; mt < 4; ++mt) {
+          T* dst = P + (mt * 8 + gq) * pitch + cw + 2 * tq;
+          if constexpr (CPLX) {
+            dst[0] = make_double2(acc[mt][0] - acc[mt][2], acc[mt][4] - acc[mt][0] - acc[mt][2]);
+            dst[1] = make_double2(acc[mt][1] - acc[mt][3], acc[mt][5] - acc[mt][1] - acc[mt][3]);
+          } else {
+            dst[0] = acc[mt][0];
+            dst[1] = acc[mt][1];
+          }
+        }
+        __syncwarp();
+        if (!bulk) {
+          // 32 rows x 8 columns: lane -> (row parity group lane >> 3, column lane & 7)
+          const int col = cw + (lane & 7);
+          if (col < len) {
+#pragma unroll 4
+            for (int q = (lane >> 3); q < JP; q += 4) {
+              const int64_t r = grow(q);
+              if (r >= 0) base[r * ld + c0 + col] = P[q * pitch + col];
             }
           }
-        } else {
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
         }
       }
-      __syncwarp();
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          T* dst = P + (mt * 8 + gq) * pitch + cw + nt * 8 + 2 * tq;
-          if constexpr (CPLX) {
-            dst[0] = make_double2(acc[mt][nt][0] - acc[mt][nt][2], acc[mt][nt][4] - acc[mt][nt][0] - acc[mt][nt][2]);
-            dst[1] = make_double2(acc[mt][nt][1] - acc[mt][nt][3], acc[mt][nt][5] - acc[mt][nt][1] - acc[mt][nt][3]);
-          } else {
-            dst[0] = acc[mt][nt][0];
-            dst[1] = acc[mt][nt][1];
-          }
+      if (bulk) {
+        // the half goes out as TMA bulk stores (one per row) once every warp has written its columns back into P
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+          const int64_t r = grow(lane);
+          if (r >= 0) bulk_s2g(base + r * ld + c0 + hbeg, P + lane * pitch + hbeg, (uint32_t)((CH / 2) * sizeof(T)));
+          bulk_commit();
+          if (h == 1) bulk_wait_read();  // P may be overwritten (next chunk) or the CTA may exit after this
         }
-      __syncwarp();
-      if (!bulk_ok(base, ld, len)) {
-        // 32 rows x 16 columns: lanes 0-15 take even rows, lanes 16-31 odd rows
-        const int col = cw + (lane & 15);
-        if (col < len) {
-#pragma unroll 4
-          for (int q = (lane >> 4); q < JP; q += 2) {
-            const int64_t r = grow(q);
-            if (r >= 0) base[r * ld + c0 + col] = P[q * pitch + col];
-          }
-        }
-      }
-    }
-    if (bulk_ok(base, ld, len)) {
-      // whole rows go out as TMA bulk stores once every warp has written its columns back into P
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (warp == 0) {
-        const int64_t r = grow(lane);
-        if (r >= 0) bulk_s2g(base + r * ld + c0, P + lane * pitch, (uint32_t)(CH * sizeof(T)));
-        bulk_commit();
-        bulk_wait_read();  // P may be overwritten (next chunk) or the CTA may exit after this
       }
     }
   };
@@ -763,7 +772,8 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   for (int gch = crank; gch < a.nx + a.nv; gch += S) {
     if (gch == resident) continue;
     __syncthreads();
-    load_chunk(gch);
+    const bool bulk = load_chunk(gch);
+    if (bulk) { wait_half(0); wait_half(1); bar_phase ^= 1; }
     __syncthreads();
     apply_chunk(gch);
   }
@@ -1028,7 +1038,9 @@ static JacobiPlan jacobi_plan(int64_t n, int64_t L, bool with_v, int batch) {
     if (chunks(ch) < c) break;
     if (c > 1 && max_active_clusters<T>(di, c, smem_for(ch)) < p.npairs * batch) continue;
     const int per = (chunks(ch) + c - 1) / c;
-    const int cost = per * ch;  // elements of a row each CTA walks through
+    // elements of a row each CTA walks through, plus the price of a larger cluster (DSMEM reduction and barriers
+    // over c CTAs, the rotation phase replicated c times) in the same unit: measured ~1 us ~ 32 elements per CTA
+    const int cost = per * ch + 32 * c;
     if (cost < best) { best = cost; S = c; CH = ch; }
   }
   // A batch that cannot be resident at one CTA per SM: shorter chunks bring the shared memory of a CTA under

@@ -503,7 +503,7 @@ def trace(a, axis1, axis2):
     oshape = [s for i, s in enumerate(a.shape) if i not in (axis1, axis2)]
     out = _empty(oshape, a.dtype)
     if out.numel():
-        if a.shape[axis1] == 0:
+        if a.shape[axis1] == 0 or a.shape[axis2] == 0:
             out.zero_()
         else:
             d = a.desc()
