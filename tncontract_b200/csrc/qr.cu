@@ -212,10 +212,14 @@ __device__ __forceinline__ void panel_right_mult(T* P, int pitch, int r_begin, i
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int r = 0; r < (CPLX ? 4 : 2); ++r) acc[nt][r] = 0.0;
-    const int row = m0 + gq;  // rows past nrows (< K4 <= pitch) read finite junk that is never stored
+    const int row = m0 + gq;
+    // lanes whose row lies past the slab load the tile's last valid row instead (their result is never stored):
+    // a row index past the pitch would alias the next column's first rows, which another warp is rewriting
+    // (racecheck, round 2) -- harmless for the stored rows, but a read of memory in flux all the same
+    const int lrow = row < nrows ? row : nrows - 1;
 #pragma unroll 2
     for (int k0 = 0; k0 < QR_NB; k0 += 4) {
-      const T av = P[(k0 + tq) * pitch + row];
+      const T av = P[(k0 + tq) * pitch + lrow];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const T bv = B[(k0 + tq) * QP + nt * 8 + gq];
