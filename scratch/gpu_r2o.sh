@@ -4,6 +4,7 @@ mkdir -p gpurun_out
 TNB_LIB_PATH=scratch/exp/libtnb_flat2.so timeout 300 python scratch/jac_time.py > gpurun_out/r2o_jac_flat.log 2>&1
 timeout 300 python scratch/jac_time.py > gpurun_out/r2o_jac_split.log 2>&1
 cat gpurun_out/r2o_jac_flat.log gpurun_out/r2o_jac_split.log
+timeout 200 python scratch/hbm_ops.py time > gpurun_out/r2o_hbm_time.log 2>&1; cat gpurun_out/r2o_hbm_time.log
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2o_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2o_pytest.log
 tail -4 gpurun_out/r2o_pytest.log
 timeout 600 python bench.py > gpurun_out/bench_r2o.json 2> gpurun_out/r2o_bench_err.log

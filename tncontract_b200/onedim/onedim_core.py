@@ -790,7 +790,7 @@ def _fused_apply_ok(a, w, mps, mpo):
             len(set(w.labels)) == 4 and len(set(a.labels)) == 3 and mps.left_label in a.labels:
         wr, d = w.index_dimension(mpo.right_label), w.index_dimension(mpo.physin_label)
         rows = a.index_dimension(mps.left_label) * w.index_dimension(mpo.left_label) * w.index_dimension(mpo.physout_label)
-        if wr * d * a.data.dtype.itemsize > 48 * 1024 or wr * d * 16 > 48 * 1024 or rows > 2 ** 31 - 1:
+        if wr * d * 16 > 48 * 1024 or rows > 2 ** 31 - 1:
             return False
     return (sorted(a.labels) == sorted([mps.phys_label, mps.left_label, mps.right_label]) and
             sorted(w.labels) == sorted([mpo.left_label, mpo.right_label, mpo.physout_label, mpo.physin_label]) and
