@@ -6,7 +6,8 @@ timeout 300 python scratch/jac_time.py > gpurun_out/r2o_jac_split.log 2>&1
 cat gpurun_out/r2o_jac_flat.log gpurun_out/r2o_jac_split.log
 TNB_LIB_PATH=scratch/exp/libtnb_notma.so timeout 200 python scratch/gemm_shapes.py > gpurun_out/r2o_gemm_notma.log 2>&1
 timeout 200 python scratch/gemm_shapes.py > gpurun_out/r2o_gemm_tma.log 2>&1
-cat gpurun_out/r2o_gemm_notma.log gpurun_out/r2o_gemm_tma.log
+TNB_LIB_PATH=scratch/exp/libtnb_sk1.so timeout 200 python scratch/gemm_shapes.py > gpurun_out/r2o_gemm_sk1.log 2>&1
+cat gpurun_out/r2o_gemm_notma.log gpurun_out/r2o_gemm_tma.log gpurun_out/r2o_gemm_sk1.log
 TNB_LIB_PATH=scratch/exp/libtnb_stamps.so timeout 120 python scratch/jac_stamps.py > gpurun_out/r2o_stamps.log 2>&1; tail -8 gpurun_out/r2o_stamps.log
 timeout 200 python scratch/hbm_ops.py time > gpurun_out/r2o_hbm_time.log 2>&1; cat gpurun_out/r2o_hbm_time.log
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2o_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2o_pytest.log

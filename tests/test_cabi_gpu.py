@@ -398,6 +398,33 @@ def test_elementwise(cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+def test_svd_split_tournament(cplx):
+    """k >= 1024 columns: the Jacobi sweeps run as a split tournament (two half-rounds on two streams, the
+    two-CTAs-per-SM build of the round kernel with its compact shared-memory layout).  Block counts that are
+    not a multiple of four (padding blocks), V accumulated (tnb_svd) and not (tnb_svd_project), and a graded
+    matrix, whose pairs take the double-precision Gram domain -- updated IN PLACE in the compact layout."""
+    torch, _lib, dv = _mods()
+    rng = np.random.default_rng(12)
+    for m, n in [(1100, 1024), (1024, 1300), (1040, 1040)]:
+        a = rnd(rng, (m, n), cplx)
+        u, s, p = dv.svd_project(dv.DevArray.from_host(a))
+        u, s, p = np.asarray(u), np.asarray(s), np.asarray(p)
+        k = min(m, n)
+        sref = np.linalg.svd(a, compute_uv=False)
+        assert np.max(np.abs(s - sref)) <= 1e-12 * sref[0]
+        assert np.linalg.norm(u.conj().T @ u - np.eye(k)) < 1e-11 * k
+        assert rel(u @ p, a) < 1e-11
+    a = rnd(rng, (1030, 1024), cplx)
+    u, s, vh = dv.svd(dv.DevArray.from_host(a))
+    _check_svd(a, np.asarray(u), np.asarray(s), np.asarray(vh))
+    g = rnd(rng, (1100, 1024), cplx) * np.logspace(0, -11, 1024)[None, :]
+    u, s, p = dv.svd_project(dv.DevArray.from_host(g))
+    sref = np.linalg.svd(g, compute_uv=False)
+    assert np.max(np.abs(np.asarray(s) - sref) / sref) < 1e-8
+    assert np.linalg.norm(np.asarray(u).conj().T @ np.asarray(u) - np.eye(1024)) < 1e-9
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_svd_project(cplx):
     """tnb_svd_project: U, S and P = U^H A = diag(S) Vh, V never accumulated."""
     torch, _lib, dv = _mods()

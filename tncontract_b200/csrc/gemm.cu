@@ -606,7 +606,12 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     const int64_t max_by_k = K / (bk * 16);  // keep >= 16 k-steps per split
     const int64_t max_by_ws = (int64_t)(splitk_bytes / ((size_t)M * N * (cplx ? 16 : 8)));
     auto plan = [&](int64_t tiles) {
-      int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;  // aim at ~2 CTAs per SM
+#ifndef TNB_EXP_SPLITK_WAVES_X2
+#define TNB_EXP_SPLITK_WAVES_X2 4   // kernel experiments: target number of CTAs in units of half the SM count
+#endif
+      // aim at ~2 CTAs per SM; the one-wave experiment rounds down so that every CTA is resident at once
+      int64_t want = TNB_EXP_SPLITK_WAVES_X2 == 2 ? (int64_t)sm_count() / tiles
+                                                  : (TNB_EXP_SPLITK_WAVES_X2 * (int64_t)sm_count() / 2 + tiles - 1) / tiles;
       if (want > max_by_k) want = max_by_k;
       if (want > max_by_ws) want = max_by_ws;
       if (want > 64) want = 64;
