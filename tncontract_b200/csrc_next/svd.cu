@@ -50,7 +50,7 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
+#include "../csrc/common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -73,6 +73,12 @@ constexpr int JGG = JP + 1;  // pitch of G (rotation phase only): row AND column
 constexpr int JWP = JP + 2;  // pitch of W (= 2 mod 8): the apply reads it transposed (fragment [k = p][m = q]) without conflicts
 constexpr int JPAD = 4;      // panel pitch = CH + JPAD for the same reason
 constexpr int MAX_SWEEPS = 60;
+// compact shared-memory layout behind the panel (units of T): offsets of the CTA's Gram partial and of W, total
+constexpr int JC_GPART = 16 * 2 * 64;
+constexpr int JC_W = 1600;
+constexpr int JC_TOTAL = JC_W + JP * JWP;
+static_assert(JC_GPART + 10 * 64 <= JC_TOTAL, "Gram partial must fit behind the slots");
+static_assert(JP * JGG + (JP * JGG + 1) / 2 <= JC_W, "G and its first single-precision copy must end before W");
 
 #ifdef TNB_EXP_STAMPS
 __device__ long long g_jac_dbg[128];  // kernel experiments: clock64 stamps of the rotation phase (CTA 0)
@@ -109,6 +115,13 @@ struct JacobiArgs {
   int64_t xstride, vstride;  // elements between consecutive matrices of a batch (blockIdx.y)
   int nblk;     // even number of column blocks (the last ones may be empty)
   int round;
+  // which block pairs a launch handles (pair index p = cluster index, round r):
+  //   sched 0: pair p of round r of the round-robin tournament over all nblk blocks
+  //   sched 1: the same tournament inside the group of gN (even) blocks starting at block gA
+  //   sched 2: bipartite -- block gA + p against block gB + (p + r) mod gN   (p, r in [0, gN))
+  // 1 and 2 are the stages of the split tournament (see jacobi()): two launches with disjoint blocks
+  // run side by side on two streams.
+  int sched, gA, gB, gN;
   int diag;     // 1: rotate the pairs INSIDE each of the two blocks (15 steps); 0: the 16 x 16 cross pairs (16 steps)
   int S;        // CTAs per cluster
   int CH;       // chunk length (power of two)
@@ -268,7 +281,7 @@ struct RotCtx {
 };
 
 template <typename T, typename GT>
-__device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename Num<GT>::real_t (*s_rc)[JP / 2],
+__device__ __forceinline__ void rotation_phase(GT* G0, GT* G1, T* W, typename Num<GT>::real_t (*s_rc)[JP / 2],
                                                GT (*s_rsp)[JP / 2], const RotCtx& cx, cg::cluster_group& cluster,
                                                unsigned& state, int warp, int lane) {
   typedef Num<T> N_;
@@ -276,8 +289,9 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
   constexpr int ROTW = JT / 32 - 1;
   constexpr int NGB = JB * (JB + 1) / 2;   // 136 blocks
   const int nsteps = cx.nsteps;
+  const bool g_inplace = (G0 == G1);
   if (warp == ROTW && lane < JP / 2) {
-    const Rot<GT> r = make_rot<GT>(G, cx.rr[0][lane][0], cx.rr[0][lane][1], cx.tol2, state);
+    const Rot<GT> r = make_rot<GT>(G0, cx.rr[0][lane][0], cx.rr[0][lane][1], cx.tol2, state);
     s_rc[0][lane] = r.c;
     s_rsp[0][lane] = r.sp;
   }
@@ -285,16 +299,28 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
   unsigned nx_ahead = (warp == ROTW && lane < JP / 2 && nsteps > 1) ? cx.nxt[0][lane] : 0u;
   // a G task keeps its block (ta, tb) through all steps
   int g_ta = 0, g_tb = 0;
-  if (cx.g0 >= 0 && cx.g0 + lane < NGB) { g_ta = cx.gt[cx.g0 + lane][0]; g_tb = cx.gt[cx.g0 + lane][1]; }
+  const bool g_on = cx.g0 >= 0 && cx.g0 + lane < NGB;
+  if (g_on) { g_ta = cx.gt[cx.g0 + lane][0]; g_tb = cx.gt[cx.g0 + lane][1]; }
   __syncthreads();
   JSTAMP(0, threadIdx.x == 0);
   for (int step = 0; step < nsteps; ++step) {
     const int cur = step & 1;
     JSTAMP(1 + 4 * step, threadIdx.x == ROTW * 32);
-    const GT* Gc = G + cur * gbuf;
-    GT* Gn = G + (cur ^ 1) * gbuf;
-    const T* Wc = W + cur * (JP * JGP);
-    T* Wn = W + (cur ^ 1) * (JP * JGP);
+    const GT* Gc = cur ? G1 : G0;
+    GT* Gn = cur ? G0 : G1;
+    // G0 == G1 (compact shared-memory layout, double-precision Gram domain): G is updated in place, so the
+    // new blocks are held in registers until the rotation warp has read what it needs of the old ones
+    const T* Wc = W;   // W' = W J touches two columns per rotation and the rotations of a step are disjoint: in place
+    T* Wn = W;
+    GT n00, n01, n10, n11;
+    int s_pa = 0, s_qa = 0, s_pb = 0, s_qb = 0;
+    auto store_block = [&](GT* Gd, int pa, int qa, int pb, int qb, bool offdiag) {
+      if (offdiag) {
+        Gd[pb * JGG + pa] = NG::conj(n00); Gd[qb * JGG + pa] = NG::conj(n01);
+        Gd[pb * JGG + qa] = NG::conj(n10); Gd[qb * JGG + qa] = NG::conj(n11);
+      }
+      Gd[pa * JGG + pb] = n00; Gd[pa * JGG + qb] = n01; Gd[qa * JGG + pb] = n10; Gd[qa * JGG + qb] = n11;
+    };
     if (warp == ROTW) {
       if (lane < JP / 2 && step + 1 < nsteps) {
         const unsigned nx_ = nx_ahead;
@@ -313,8 +339,7 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
       }
       JSTAMP(2 + 4 * step, lane == 0);
     } else if (cx.g0 >= 0) {
-      const int t = cx.g0 + lane;
-      if (t < NGB) {
+      if (g_on) {
         const int ta = g_ta, tb = g_tb;
         const int pa = cx.rr[step][ta][0], qa = cx.rr[step][ta][1];
         const int pb = cx.rr[step][tb][0], qb = cx.rr[step][tb][1];
@@ -328,18 +353,16 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
         const GT t10 = rot_mix(Rb.c, b10, msb, b11), t11 = rot_mix(Rb.c, b11, Rb.sp, b10);
         // B' = J_a^H T1,  J_a^H = [[c, -sp], [conj(sp), c]]
         const GT msa = NG::sub(NG::zero(), Ra.sp), csa = NG::conj(Ra.sp);
-        GT n00 = rot_mix(Ra.c, t00, msa, t10), n01 = rot_mix(Ra.c, t01, msa, t11);
-        GT n10 = rot_mix(Ra.c, t10, csa, t00), n11 = rot_mix(Ra.c, t11, csa, t01);
+        n00 = rot_mix(Ra.c, t00, msa, t10); n01 = rot_mix(Ra.c, t01, msa, t11);
+        n10 = rot_mix(Ra.c, t10, csa, t00); n11 = rot_mix(Ra.c, t11, csa, t01);
         if (ta == tb) {
           // diagonal block: real diagonal, exact zero where a rotation was applied
           n00 = NG::from(NG::real(n00), 0);
           n11 = NG::from(NG::real(n11), 0);
           if (Ra.c != 1 || NG::abs2(Ra.sp) != 0) { n01 = NG::zero(); n10 = NG::zero(); }
-        } else {
-          Gn[pb * JGG + pa] = NG::conj(n00); Gn[qb * JGG + pa] = NG::conj(n01);
-          Gn[pb * JGG + qa] = NG::conj(n10); Gn[qb * JGG + qa] = NG::conj(n11);
         }
-        Gn[pa * JGG + pb] = n00; Gn[pa * JGG + qb] = n01; Gn[qa * JGG + pb] = n10; Gn[qa * JGG + qb] = n11;
+        if (!g_inplace) store_block(Gn, pa, qa, pb, qb, ta != tb);
+        else { s_pa = pa; s_qa = qa; s_pb = pb; s_qb = qb; }
       }
       JSTAMP(3 + 4 * step, threadIdx.x == 0);
     } else if (cx.wi >= 0) {
@@ -364,6 +387,10 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
       }
       JSTAMP(4 + 4 * step, lane == 0 && cx.wi == 0);
     }
+    if (g_inplace) {   // uniform over the CTA
+      __syncthreads();
+      if (warp != ROTW && g_on) store_block(Gn, s_pa, s_qa, s_pb, s_qb, g_ta != g_tb);
+    }
     __syncthreads();
   }
   JSTAMP(1 + 4 * nsteps, threadIdx.x == 0);
@@ -372,8 +399,10 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
 
 
 // Shared memory: P[JP][CH+JPAD] | G[2][JP][JGP] | W[2][JP][JGP]  (the cluster-reduction partials live in W's space)
-template <typename T>
-__global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
+// COMPACT: the two-CTAs-per-SM build of the kernel (split tournament): compact shared-memory layout and at most
+// 64 registers per thread (the apply phase then works on two 16-row halves of its 32 x 8 output block).
+template <typename T, bool COMPACT>
+__global__ void __launch_bounds__(JT, COMPACT ? 2 : 1) jacobi_round_kernel(JacobiArgs a) {
   typedef Num<T> N_;
   constexpr bool CPLX = (sizeof(T) == 16);
   JSTAMP(70, threadIdx.x == 0);
@@ -382,15 +411,30 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   const int crank = (int)cluster.block_rank();
   const int pair = blockIdx.x / S;
   int bI, bJ;
-  rr_pair(a.nblk, a.round, pair, bI, bJ);
+  if (a.sched == 0) {
+    rr_pair(a.nblk, a.round, pair, bI, bJ);
+  } else if (a.sched == 1) {
+    rr_pair(a.gN, a.round, pair, bI, bJ);
+    bI += a.gA; bJ += a.gA;
+  } else {
+    bI = a.gA + pair;
+    bJ = a.gB + (pair + a.round) % a.gN;
+  }
   if (bI > bJ) { const int t = bI; bI = bJ; bJ = t; }
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = a.CH, pitch = CH + JPAD;
   T* P = reinterpret_cast<T*>(smem_raw);
-  T* G = P + (size_t)JP * pitch;   // G and W are double-buffered through the sweep: [2][JP][JGP] each
-  T* W = G + 2 * JP * JGP;
-  T* Gpart = W;
+  // Behind the panel, in units of T (see jacobi_smem_elems):
+  //   roomy   (one CTA per SM):  G [2][JP][JGP] | W [JP][JGP] (+ one spare buffer)
+  //   compact (two CTAs per SM): everything overlaid on its predecessor in time --
+  //     slots [16][2][64] at 0 | Gpart [10][64] at 2048          (Gram partials of the warps / of this CTA)
+  //     G [JP][JGG] at 0, its single-precision copies at JP*JGG (first) and at 0 (second, over G itself)
+  //     W [JP][JWP] at 1600 (over Gpart, once the cluster has read it)
+  //   In the compact layout a double-precision Gram domain has ONE buffer (updated in place, one more barrier per step).
+  T* G = P + (size_t)JP * pitch;
+  T* W = COMPACT ? G + JC_W : G + 2 * JP * JGP;
+  T* Gpart = COMPACT ? G + JC_GPART : W;   // [GRAM_TILES][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   // s_rr[step][a] = (smaller, larger) panel column of rotation pair a in step `step`.
@@ -586,7 +630,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     T sum = N_::zero();
     for (int w = (8 * t) / GRAM_UPW; w <= (8 * t + 7) / GRAM_UPW; ++w)
       sum = N_::add(sum, slots[(w * 2 + ((((w * GRAM_UPW) >> 3) == t) ? 0 : 1)) * 64 + e]);
-    Gpart[(gm * 8 + (e >> 3)) * JGP + gn * 8 + (e & 7)] = sum;
+    Gpart[idx] = sum;
   }
   cluster.sync();
   // sum of the cluster's partials (same order in every CTA: identical bits everywhere), mirrored into
@@ -599,7 +643,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     if (i > j) continue;
     T part[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) part[q] = (q < S) ? cluster.map_shared_rank(Gpart, q)[i * JGP + j] : N_::zero();
+    for (int q = 0; q < 8; ++q) part[q] = (q < S) ? cluster.map_shared_rank(Gpart, q)[idx] : N_::zero();
     T sum = part[0];
 #pragma unroll
     for (int q = 1; q < 8; ++q) sum = N_::add(sum, part[q]);
@@ -665,19 +709,20 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   }
   if (use32) {
     typedef typename LowPrec<T>::type GT;
-    GT* G32 = reinterpret_cast<GT*>(G + JP * JGP);     // two single-precision buffers inside G's second buffer
+    // two single-precision buffers: roomy -- both inside G's second buffer; compact -- behind G and over G itself
+    GT* G32a = reinterpret_cast<GT*>(G + (COMPACT ? JP * JGG : JP * JGP));
+    GT* G32b = COMPACT ? reinterpret_cast<GT*>(G) : G32a + JP * JGG;
     for (int idx = tid; idx < JP * JP; idx += JT) {
       const int i = idx / JP, j = idx - i * JP;
       const T v = N_::scale(G[i * JGG + j], gscale);
-      if constexpr (CPLX) G32[i * JGG + j] = make_float2((float)v.x, (float)v.y); else G32[i * JGG + j] = (float)v;
+      if constexpr (CPLX) G32a[i * JGG + j] = make_float2((float)v.x, (float)v.y); else G32a[i * JGG + j] = (float)v;
     }
     __syncthreads();
-    rotation_phase<T, GT>(G32, JP * JGG, W, reinterpret_cast<float (*)[JP / 2]>(s_rc),
+    rotation_phase<T, GT>(G32a, G32b, W, reinterpret_cast<float (*)[JP / 2]>(s_rc),
                           reinterpret_cast<GT (*)[JP / 2]>(s_rsp), cx, cluster, state, warp, lane);
   } else {
-    rotation_phase<T, T>(G, JP * JGP, W, s_rc, s_rsp, cx, cluster, state, warp, lane);
+    rotation_phase<T, T>(G, COMPACT ? G : G + JP * JGP, W, s_rc, s_rsp, cx, cluster, state, warp, lane);
   }
-  W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
 #endif
   JSTAMP(75, threadIdx.x == 0);
   if (crank == 0) {
@@ -701,44 +746,72 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         if (cw >= len) break;
         // complex: 3-multiplication form, P1 = wr pr, P2 = wi pi, P3 = (wr + wi)(pr + pi):
         //   re = P1 - P2,  im = P3 - P1 - P2   (12 DMMAs per k-step instead of 16)
-        double acc[4][CPLX ? 6 : 2];
+        // MTH row tiles of 8 at a time: all 4 (one pass over k), or 2 + 2 in the 64-register build -- the second
+        // pass re-reads the same columns of P, so nothing of a pass is written back before both are done
+        constexpr int MTH = COMPACT ? 2 : 4;
+        T res[2][2];   // COMPACT: results of the first pass (row tiles 0, 1), held until the second is done
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mh = 0; mh < 4 / MTH; ++mh) {
+          double acc[MTH][CPLX ? 6 : 2];
 #pragma unroll
-          for (int r = 0; r < (CPLX ? 6 : 2); ++r) acc[mt][r] = 0.0;
+          for (int mt = 0; mt < MTH; ++mt)
+#pragma unroll
+            for (int r = 0; r < (CPLX ? 6 : 2); ++r) acc[mt][r] = 0.0;
 #ifdef TNB_EXP_SKIP_APPLY
-        for (int k0 = 0; k0 < 4; k0 += 4) {
+          for (int k0 = 0; k0 < 4; k0 += 4) {
 #else
 #pragma unroll 2
-        for (int k0 = 0; k0 < JP; k0 += 4) {
+          for (int k0 = 0; k0 < JP; k0 += 4) {
 #endif
-          T av[4];
+            T av[MTH];
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) av[mt] = W[(k0 + tq) * JWP + mt * 8 + gq];
-          const T bv = P[(k0 + tq) * pitch + cw + gq];
-          if constexpr (CPLX) {
-            const double bs = bv.x + bv.y;
+            for (int mt = 0; mt < MTH; ++mt) av[mt] = W[(k0 + tq) * JWP + (mh * MTH + mt) * 8 + gq];
+            const T bv = P[(k0 + tq) * pitch + cw + gq];
+            if constexpr (CPLX) {
+              const double bs = bv.x + bv.y;
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-              dmma884(acc[mt][0], acc[mt][1], av[mt].x, bv.x);
-              dmma884(acc[mt][2], acc[mt][3], av[mt].y, bv.y);
-              dmma884(acc[mt][4], acc[mt][5], av[mt].x + av[mt].y, bs);
+              for (int mt = 0; mt < MTH; ++mt) {
+                dmma884(acc[mt][0], acc[mt][1], av[mt].x, bv.x);
+                dmma884(acc[mt][2], acc[mt][3], av[mt].y, bv.y);
+                dmma884(acc[mt][4], acc[mt][5], av[mt].x + av[mt].y, bs);
+              }
+            } else {
+#pragma unroll
+              for (int mt = 0; mt < MTH; ++mt) dmma884(acc[mt][0], acc[mt][1], av[mt], bv);
             }
-          } else {
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][0], acc[mt][1], av[mt], bv);
           }
-        }
-        __syncwarp();
+          if (COMPACT && mh == 0) {
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          T* dst = P + (mt * 8 + gq) * pitch + cw + 2 * tq;
-          if constexpr (CPLX) {
-            dst[0] = make_double2(acc[mt][0] - acc[mt][2], acc[mt][4] - acc[mt][0] - acc[mt][2]);
-            dst[1] = make_double2(acc[mt][1] - acc[mt][3], acc[mt][5] - acc[mt][1] - acc[mt][3]);
-          } else {
-            dst[0] = acc[mt][0];
-            dst[1] = acc[mt][1];
+            for (int mt = 0; mt < MTH; ++mt) {
+              if constexpr (CPLX) {
+                res[mt & 1][0] = make_double2(acc[mt][0] - acc[mt][2], acc[mt][4] - acc[mt][0] - acc[mt][2]);
+                res[mt & 1][1] = make_double2(acc[mt][1] - acc[mt][3], acc[mt][5] - acc[mt][1] - acc[mt][3]);
+              } else {
+                res[mt & 1][0] = acc[mt][0];
+                res[mt & 1][1] = acc[mt][1];
+              }
+            }
+            continue;
+          }
+          __syncwarp();
+          if (COMPACT) {
+#pragma unroll
+            for (int mt = 0; mt < MTH; ++mt) {
+              T* dst = P + (mt * 8 + gq) * pitch + cw + 2 * tq;
+              dst[0] = res[mt & 1][0];
+              dst[1] = res[mt & 1][1];
+            }
+          }
+#pragma unroll
+          for (int mt = 0; mt < MTH; ++mt) {
+            T* dst = P + ((mh * MTH + mt) * 8 + gq) * pitch + cw + 2 * tq;
+            if constexpr (CPLX) {
+              dst[0] = make_double2(acc[mt][0] - acc[mt][2], acc[mt][4] - acc[mt][0] - acc[mt][2]);
+              dst[1] = make_double2(acc[mt][1] - acc[mt][3], acc[mt][5] - acc[mt][1] - acc[mt][3]);
+            } else {
+              dst[0] = acc[mt][0];
+              dst[1] = acc[mt][1];
+            }
           }
         }
         __syncwarp();
@@ -915,10 +988,10 @@ static SvdLayout svd_layout(int dtype, int64_t m, int64_t n) {
 // `smem` bytes each) it can hold at once.
 struct JacobiDeviceInfo {
   std::mutex mu;
-  bool configured[2] = {false, false};
-  int clusters[2][9][16];   // [dtype][S][smem / 16 KB], -1 = not yet queried
+  bool configured[2][2] = {{false, false}, {false, false}};   // [dtype][compact]
+  int clusters[2][2][9][16];   // [dtype][compact][S][smem / 16 KB], -1 = not yet queried
   int last_sweeps[2] = {0, 0};  // sweeps the previous factorisation of this dtype needed (queueing hint)
-  JacobiDeviceInfo() { for (auto& d : clusters) for (auto& r : d) for (int& v : r) v = -1; }
+  JacobiDeviceInfo() { for (auto& d : clusters) for (auto& c : d) for (auto& r : c) for (int& v : r) v = -1; }
 };
 static JacobiDeviceInfo& jacobi_device_info() {
   static JacobiDeviceInfo info[64];
@@ -927,23 +1000,24 @@ static JacobiDeviceInfo& jacobi_device_info() {
   return info[(dev >= 0 && dev < 64) ? dev : 0];
 }
 
-template <typename T>
+template <typename T, bool COMPACT>
 static int configure_round_kernel(JacobiDeviceInfo& di) {
   constexpr int dt = sizeof(T) == 16 ? 1 : 0;
-  if (di.configured[dt]) return 0;
-  TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
-  di.configured[dt] = true;
+  if (di.configured[dt][COMPACT]) return 0;
+  TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (COMPACT ? 112 : 220) * 1024));
+  TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T, COMPACT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+  di.configured[dt][COMPACT] = true;
   return 0;
 }
 
-template <typename T>
+template <typename T, bool COMPACT>
 static int max_active_clusters(JacobiDeviceInfo& di, int S, size_t smem) {
   constexpr int dt = sizeof(T) == 16 ? 1 : 0;
   const int slot = (int)(smem >> 14) < 16 ? (int)(smem >> 14) : 15;
   std::lock_guard<std::mutex> lock(di.mu);
-  if (di.clusters[dt][S][slot] >= 0) return di.clusters[dt][S][slot];
-  if (configure_round_kernel<T>(di) != 0) { cudaGetLastError(); return 0; }
+  if (di.clusters[dt][COMPACT][S][slot] >= 0) return di.clusters[dt][COMPACT][S][slot];
+  if (configure_round_kernel<T, COMPACT>(di) != 0) { cudaGetLastError(); return 0; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(S * 64), 1, 1);
   cfg.blockDim = dim3(JT, 1, 1);
@@ -956,14 +1030,14 @@ static int max_active_clusters(JacobiDeviceInfo& di, int S, size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, jacobi_round_kernel<T>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-  di.clusters[dt][S][slot] = n;
+  if (cudaOccupancyMaxActiveClusters(&n, jacobi_round_kernel<T, COMPACT>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  di.clusters[dt][COMPACT][S][slot] = n;
   return n;
 }
 
 // Every launch of the Jacobi chain carries the programmatic-stream-serialization attribute: the kernels wait
 // for their predecessor themselves (griddep_wait), after their prologue.
-template <typename T>
+template <typename T, bool COMPACT = false>
 static int launch_round(JacobiArgs& a, int npairs, int batch, size_t smem, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(npairs * a.S), (unsigned)batch, 1);
@@ -983,7 +1057,7 @@ static int launch_round(JacobiArgs& a, int npairs, int batch, size_t smem, cudaS
 #else
   cfg.numAttrs = 2;
 #endif
-  TNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, jacobi_round_kernel<T>, a));
+  TNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, jacobi_round_kernel<T, COMPACT>, a));
   count_launch();
   return 0;
 }
@@ -1008,7 +1082,7 @@ static int launch_finish_sweep(JacobiFlags* flags, int batch, cudaStream_t st) {
 }
 
 // Geometry of the round launches for n columns of length L (plus n more of V when with_v).
-struct JacobiPlan { int nblk, npairs, rounds, S, CH, nx, nv; size_t smem; };
+struct JacobiPlan { int nblk, npairs, rounds, S, CH, nx, nv, compact; size_t smem; };
 
 template <typename T>
 static JacobiPlan jacobi_plan(int64_t n, int64_t L, bool with_v, int batch) {
@@ -1036,7 +1110,7 @@ static JacobiPlan jacobi_plan(int64_t n, int64_t L, bool with_v, int batch) {
     int ch = ch_top;
     while (ch > 32 && chunks(ch) < c) ch /= 2;
     if (chunks(ch) < c) break;
-    if (c > 1 && max_active_clusters<T>(di, c, smem_for(ch)) < p.npairs * batch) continue;
+    if (c > 1 && max_active_clusters<T, false>(di, c, smem_for(ch)) < p.npairs * batch) continue;
     const int per = (chunks(ch) + c - 1) / c;
     // elements of a row each CTA walks through, plus the price of a larger cluster (DSMEM reduction and barriers
     // over c CTAs, the rotation phase replicated c times) in the same unit: measured ~1 us ~ 32 elements per CTA
@@ -1047,15 +1121,135 @@ static JacobiPlan jacobi_plan(int64_t n, int64_t L, bool with_v, int batch) {
   // half an SM's, so that two CTAs (of different matrices) share an SM and one's rotation phase overlaps the
   // other's tensor-core phases.  Costs a second pass over the chunks that are not resident (L2 traffic only).
 #ifndef TNB_EXP_NO_BATCH_HALVING
+  p.compact = 0;
   if (batch > 1 && S == 1 && (int64_t)p.npairs * batch > (int64_t)sm_count()) {
-    while (CH > 64 && smem_for(CH) > 110 * 1024) CH /= 2;
+    // the two-CTAs-per-SM build of the kernel (64 registers, compact layout)
+    auto smem_compact = [&](int ch) { return ((size_t)JP * (ch + JPAD) + (size_t)JC_TOTAL) * sizeof(T); };
+    while (CH > 64 && smem_compact(CH) > 109 * 1024) CH /= 2;
+    if (smem_compact(CH) <= 109 * 1024) p.compact = 1;
   }
 #endif
   p.S = S; p.CH = CH;
   p.nx = (int)((L + CH - 1) / CH);
   p.nv = with_v ? (int)((n + CH - 1) / CH) : 0;
-  p.smem = smem_for(CH);
+  p.smem = p.compact ? ((size_t)JP * (CH + JPAD) + (size_t)JC_TOTAL) * sizeof(T) : smem_for(CH);
   return p;
+}
+
+// ---- split tournament: two independent halves of a round on two streams -------------------------------------
+// A round is latency-bound (load -> Gram -> cluster reduction -> 16 dependent rotation steps -> apply -> store;
+// only about a third of it is DMMA issue time) and all its clusters walk through the phases in lock-step, one
+// CTA per SM.  The split tournament orders the block pairs of a sweep so that there are always two sets of
+// pairs that do not depend on each other for a whole STAGE of rounds; each set is launched on its own stream
+// with half the pairs and CTAs small enough for two to share an SM, so one set's rotation steps run under the
+// other set's tensor-core and copy phases.  With the blocks cut into quarters A1 A2 | B1 B2 (q blocks each):
+//   stage 0   stream 0: in-block round + round-robin inside A = A1 u A2      stream 1: the same inside B
+//   stage 1   stream 0: A1 x B1 (bipartite, q rounds)                        stream 1: A2 x B2
+//   stage 2   stream 0: A1 x B2                                              stream 1: A2 x B1
+// Every block pair still meets exactly once per sweep (2q - 1 + q + q = 4q - 1 cross rounds of q pairs per
+// stream); the streams only meet at the three stage boundaries and at the end of the sweep.
+struct JacobiSide {
+  int dev = -1;
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+  int get(int device) {
+    if (dev == device && s) return 0;
+    TNB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    TNB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+    TNB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+    dev = device;
+    return 0;
+  }
+};
+static thread_local JacobiSide g_jacobi_side;
+
+#ifndef TNB_EXP_SPLIT
+#define TNB_EXP_SPLIT 1
+#endif
+#ifndef TNB_EXP_SPLIT_MIN_N
+#define TNB_EXP_SPLIT_MIN_N 512
+#endif
+
+// Geometry of the split tournament, or false when it does not apply (small matrices, or the two sets cannot
+// be resident together at two CTAs per SM).
+template <typename T>
+static bool jacobi_plan_split(int64_t n, int64_t L, bool with_v, JacobiPlan& p) {
+  if (!TNB_EXP_SPLIT || n < TNB_EXP_SPLIT_MIN_N) return false;
+  JacobiDeviceInfo& di = jacobi_device_info();
+  const int64_t nblk_real = (n + JB - 1) / JB;
+  p.nblk = (int)((nblk_real + 3) / 4 * 4);
+  const int q = p.nblk / 4;
+  p.npairs = q;           // per launch
+  p.rounds = p.nblk - 1;  // cross rounds per stream and sweep (plus the in-block round)
+  auto chunks = [&](int ch) { return (int)((L + ch - 1) / ch) + (with_v ? (int)((n + ch - 1) / ch) : 0); };
+  auto smem_for = [&](int ch) { return ((size_t)JP * (ch + JPAD) + (size_t)JC_TOTAL) * sizeof(T); };   // compact layout
+  const size_t smem_cap = 109 * 1024;   // two CTAs per SM (228 KB, 1 KB reserved and ~3 KB static each)
+  int ch_top = 32;
+  while (ch_top * 2 <= 512 && smem_for(ch_top * 2) <= smem_cap) ch_top *= 2;
+  int S = 0, CH = 0, best = 1 << 30;
+#ifdef TNB_EXP_SPLIT_S
+  for (int c = TNB_EXP_SPLIT_S; c <= TNB_EXP_SPLIT_S; ++c) {
+#else
+  for (int c = 1; c <= 8; ++c) {
+#endif
+    int ch = ch_top;
+    while (ch > 32 && chunks(ch) < c) ch /= 2;
+    if (chunks(ch) < c) break;
+    // both sets resident at once, and enough CTAs for two per SM on most of the device
+    if (max_active_clusters<T, true>(di, c, smem_for(ch)) < 2 * q) continue;
+    if (2 * q * c < sm_count() + sm_count() / 2) continue;
+    const int per = (chunks(ch) + c - 1) / c;
+    const int cost = per * ch + 32 * c;
+    if (cost < best) { best = cost; S = c; CH = ch; }
+  }
+  if (S == 0) return false;
+  p.S = S; p.CH = CH;
+  p.nx = (int)((L + CH - 1) / CH);
+  p.nv = with_v ? (int)((n + CH - 1) / CH) : 0;
+  p.smem = smem_for(CH);
+  p.compact = 1;
+  return true;
+}
+
+// One sweep of the split tournament: stream 0 = st, stream 1 = side.s.  The caller has made side.s wait for
+// everything queued on st so far; on return st waits for side.s.
+template <typename T>
+static int launch_split_sweep(JacobiArgs a, const JacobiPlan& p, size_t smem, JacobiSide& side, cudaStream_t st) {
+  const int q = p.nblk / 4, h = p.nblk / 2;
+  cudaStream_t str[2] = {st, side.s};
+  auto meet = [&]() -> int {   // each stream waits for what the other has queued so far
+    TNB_CUDA_CHECK(cudaEventRecord(side.ev_main, st));
+    TNB_CUDA_CHECK(cudaEventRecord(side.ev_side, side.s));
+    TNB_CUDA_CHECK(cudaStreamWaitEvent(st, side.ev_side, 0));
+    TNB_CUDA_CHECK(cudaStreamWaitEvent(side.s, side.ev_main, 0));
+    return 0;
+  };
+  int rc;
+  // stage 0: inside A / inside B
+  for (int r = -1; r < h - 1; ++r) {
+    for (int t = 0; t < 2; ++t) {
+      a.sched = 1; a.gA = t * h; a.gB = 0; a.gN = h;
+      a.diag = (r < 0); a.round = (r < 0) ? 0 : r;
+      rc = launch_round<T, true>(a, q, 1, smem, str[t]);
+      if (rc) return rc;
+    }
+  }
+  for (int stage = 0; stage < 2; ++stage) {
+    rc = meet();
+    if (rc) return rc;
+    for (int r = 0; r < q; ++r) {
+      for (int t = 0; t < 2; ++t) {
+        a.sched = 2; a.gN = q; a.diag = 0; a.round = r;
+        a.gA = t * q;                             // A1 on stream 0, A2 on stream 1
+        a.gB = h + ((t ^ stage) ? q : 0);         // stage 0: A1 x B1, A2 x B2;  stage 1: A1 x B2, A2 x B1
+        rc = launch_round<T, true>(a, q, 1, smem, str[t]);
+        if (rc) return rc;
+      }
+    }
+  }
+  TNB_CUDA_CHECK(cudaEventRecord(side.ev_side, side.s));
+  TNB_CUDA_CHECK(cudaStreamWaitEvent(st, side.ev_side, 0));
+  return 0;
 }
 
 // Orthogonalise the rows-as-columns of `batch` matrices Xt (n x L each, `xstride` elements apart) in place,
@@ -1074,11 +1268,27 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, int64_t xstride, T* Vt, int64_t
   JacobiDeviceInfo& di = jacobi_device_info();
   {
     std::lock_guard<std::mutex> lock(di.mu);
-    int rc = configure_round_kernel<T>(di);
+    int rc = configure_round_kernel<T, false>(di);
+    if (rc) return rc;
+    rc = configure_round_kernel<T, true>(di);
     if (rc) return rc;
   }
-  const JacobiPlan p = jacobi_plan<T>(n, L, Vt != nullptr, batch);
+  JacobiPlan p = jacobi_plan<T>(n, L, Vt != nullptr, batch);
+  bool split = false;
+  JacobiSide& side = g_jacobi_side;
+  if (batch == 1) {
+    JacobiPlan ps;
+    if (jacobi_plan_split<T>(n, L, Vt != nullptr, ps)) {
+      int dev = 0;
+      TNB_CUDA_CHECK(cudaGetDevice(&dev));
+      int rc = side.get(dev);
+      if (rc) return rc;
+      p = ps;
+      split = true;
+    }
+  }
   JacobiArgs a;
+  a.sched = 0; a.gA = 0; a.gB = 0; a.gN = 0;
   a.X = Xt; a.V = Vt; a.n = n; a.L = L; a.ldx = ldx; a.ldv = n; a.nblk = p.nblk; a.flags = flags;
   a.xstride = xstride; a.vstride = vstride;
   a.tol = sqrt((double)(L > 1 ? L : 1)) * 2.220446049250313e-16;
@@ -1092,7 +1302,7 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, int64_t xstride, T* Vt, int64_t
   // conventional flop count of one sweep (full JP x JP Gram over L, W applied over L [+ n with V]; 8 real
   // flops per complex multiply-add): what the profile credits per EXECUTED sweep
   const double sweep_flops = (cplx ? 8.0 : 2.0) * (double)JP * JP * (2.0 * (double)L + (Vt ? (double)n : 0.0)) *
-                             (double)p.npairs * (double)(p.rounds + 1);
+                             (double)(p.nblk / 2) * (double)p.nblk;
   int hint;
   {
     std::lock_guard<std::mutex> lock(di.mu);
@@ -1107,11 +1317,20 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, int64_t xstride, T* Vt, int64_t
     {
       ProfScope prof(KC_JACOBI, st, 0.0);
       for (int s = 0; s < nq; ++s) {
-        for (int r = -1; r < p.rounds; ++r) {
-          a.diag = (r < 0);           // first the pairs inside the blocks (paired up as in round 0) ...
-          a.round = (r < 0) ? 0 : r;  // ... then every block against every other block
-          int rc = launch_round<T>(a, p.npairs, batch, p.smem, st);
+        if (split) {
+          // the side stream joins in after everything queued on st so far (the previous sweep's closing kernel)
+          TNB_CUDA_CHECK(cudaEventRecord(side.ev_main, st));
+          TNB_CUDA_CHECK(cudaStreamWaitEvent(side.s, side.ev_main, 0));
+          int rc = launch_split_sweep<T>(a, p, p.smem, side, st);
           if (rc) return rc;
+        } else {
+          for (int r = -1; r < p.rounds; ++r) {
+            a.diag = (r < 0);           // first the pairs inside the blocks (paired up as in round 0) ...
+            a.round = (r < 0) ? 0 : r;  // ... then every block against every other block
+            int rc = p.compact ? launch_round<T, true>(a, p.npairs, batch, p.smem, st)
+                               : launch_round<T, false>(a, p.npairs, batch, p.smem, st);
+            if (rc) return rc;
+          }
         }
         int rc = launch_finish_sweep(flags, batch, st);
         if (rc) return rc;
