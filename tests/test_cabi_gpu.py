@@ -398,11 +398,10 @@ def test_elementwise(cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
-def test_svd_split_tournament(cplx):
-    """k >= 1024 columns: the Jacobi sweeps run as a split tournament (two half-rounds on two streams, the
-    two-CTAs-per-SM build of the round kernel with its compact shared-memory layout).  Block counts that are
-    not a multiple of four (padding blocks), V accumulated (tnb_svd) and not (tnb_svd_project), and a graded
-    matrix, whose pairs take the double-precision Gram domain -- updated IN PLACE in the compact layout."""
+def test_svd_1024_columns(cplx):
+    """k >= 1024 columns, the size class of the cfg 3 bulk sites: clusters of four CTAs per block pair, block
+    counts with and without padding blocks, V accumulated (tnb_svd) and not (tnb_svd_project), and a graded
+    matrix, whose pairs take the double-precision Gram domain."""
     torch, _lib, dv = _mods()
     rng = np.random.default_rng(12)
     for m, n in [(1100, 1024), (1024, 1300), (1040, 1040)]:

@@ -20,7 +20,17 @@
 //   K-contiguous : pitch BK+4 (real) / BK+4 (complex)
 //   MN-contiguous: pitch BMN+4 (real) / BMN+2 (complex)
 // Conjugation of either operand is a sign flip on the imaginary fragment.
+//
+// The full-size complex128 tile (the one that carries the sweeps) is fed by TMA instead
+// (gemm_tma_kernel): cp.async.bulk.tensor copies through two tensor maps (SASS UTMALDG), issued by
+// one thread, completing on per-stage mbarriers; six stages of dense 128-byte-swizzled tiles (no
+// padding: 24 KB per stage instead of 36).  Bank conflicts are avoided by the hardware swizzle plus
+// a fixed permutation of the rows inside every group of 8 (see sigma8), edges by the zero fill of
+// out-of-bounds boxes.  Anything a tensor map cannot describe (zero or unaligned strides) takes
+// the cp.async kernel.
 // Algorithmic work: 2*M*N*K flop (real), 8*M*N*K flop (complex).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace tnb {
@@ -264,6 +274,237 @@ static int launch_gemm(GemmArgs& g, int64_t batch, cudaStream_t st) {
   return 0;
 }
 
+// ---- TMA-fed variant of the full-size complex tile ---------------------------------------------------
+// Shared memory per stage: A tile 128 x 8 complex (16 KB) | B tile 64 x 8 complex (8 KB), dense, as the TMA
+// boxes land with CU_TENSOR_MAP_SWIZZLE_128B: inside every 1 KB atom (8 rows of 128 bytes) the 16-byte
+// chunk index is XORed with the row index.
+//   K-contiguous operand  ([mn][k] in global): one box {8 k, BMN rows}: row = mn, chunk = k
+//   MN-contiguous operand ([k][mn] in global): BMN / 8 boxes {8 mn, 8 k rows} of 1 KB: box = mn / 8,
+//                                              row = k, chunk = mn % 8
+// A DMMA fragment load is one 16-byte element per lane, row/column index gq = lane / 4, k index tq = lane % 4,
+// served a quarter-warp (gq in {2i, 2i+1}, tq = 0..3) at a time.  In both layouts the chunk a lane reads is
+// (index of gq's row inside its group of 8) XOR (k inside the stage); with the natural assignment the two rows of
+// a quarter-warp differ in bit 0 only and collide on the same four chunks.  So fragment row gq is mapped to
+// tile row sigma8(gq) = 4 (gq & 1) + (gq >> 1) inside its group of 8 -- the two rows then differ in bit 2 and
+// the eight lanes cover all eight chunks.  The epilogue writes C through the same permutation.
+constexpr int TMA_STAGES = 6;
+constexpr int TMA_A_BYTES = 128 * 8 * 16, TMA_B_BYTES = 64 * 8 * 16, TMA_STAGE_BYTES = TMA_A_BYTES + TMA_B_BYTES;
+__host__ __device__ __forceinline__ int sigma8(int g) { return ((g & 1) << 2) | (g >> 1); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// bounded wait: a tensor map the hardware rejects would otherwise hang the grid
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256) gemm_tma_kernel(GemmArgs g, const __grid_constant__ CUtensorMap mapA,
+                                                       const __grid_constant__ CUtensorMap mapB) {
+  typedef double2 T;
+  constexpr int BM = 128, BN = 64, BK = 8, WM = 32, WN = 32, WARPS_N = 2;
+  constexpr int MT = WM / 8, NT = WN / 8;
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  // the swizzle atoms are 1 KB: align the stage buffers in the shared-memory window (the launch adds 1 KB of slack)
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full[TMA_STAGES];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3, sg = sigma8(gq);
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const int tile = blockIdx.x;
+  const int tm = tile % g.tiles_m, tn = tile / g.tiles_m;
+  const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+  const int bz = (int)blockIdx.y;
+  T* Cg = reinterpret_cast<T*>(g.C) + (int64_t)bz * g.sC;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_per_split;
+  const int64_t kend = (g.splits > 1 && kbeg + g.k_per_split < g.K) ? kbeg + g.k_per_split : g.K;
+  int64_t ldc = g.ldc;
+  if (g.splits > 1) {
+    Cg = reinterpret_cast<T*>(g.part) + (int64_t)blockIdx.z * g.M * g.N;
+    ldc = g.N;
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  double acc[MT][NT][6];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[i][j][r] = 0.0;
+
+  const int KT = (int)((kend - kbeg + BK - 1) / BK);   // split boundaries are multiples of BK; the tail is zero-filled
+  auto issue = [&](int kt) {   // thread 0 only
+    const int s = kt % TMA_STAGES;
+    unsigned char* a_s = smem_raw + s * TMA_STAGE_BYTES;
+    unsigned char* b_s = a_s + TMA_A_BYTES;
+    const int k0 = (int)(kbeg + (int64_t)kt * BK);
+    mbar_arrive_expect_tx(&full[s], TMA_STAGE_BYTES);
+    if constexpr (A_KC) {
+      tma_load_3d(a_s, &mapA, 2 * k0, (int)m0, bz, &full[s]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BM / 8; ++j) tma_load_3d(a_s + j * 1024, &mapA, 2 * ((int)m0 + 8 * j), k0, bz, &full[s]);
+    }
+    if constexpr (B_KC) {
+      tma_load_3d(b_s, &mapB, 2 * k0, (int)n0, bz, &full[s]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN / 8; ++j) tma_load_3d(b_s + j * 1024, &mapB, 2 * ((int)n0 + 8 * j), k0, bz, &full[s]);
+    }
+  };
+  if (tid == 0) {
+    for (int s = 0; s < TMA_STAGES && s < KT; ++s) issue(s);
+  }
+  const double sgnA = g.conjA ? -1.0 : 1.0, sgnB = g.conjB ? -1.0 : 1.0;
+
+  for (int kt = 0; kt < KT; ++kt) {
+    const int s = kt % TMA_STAGES;
+    mbar_wait_bounded(&full[s], (uint32_t)((kt / TMA_STAGES) & 1));
+    const unsigned char* a_s = smem_raw + s * TMA_STAGE_BYTES;
+    const unsigned char* b_s = a_s + TMA_A_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      const int k = kk + tq, ch = ((k ^ sg) << 4);
+      T af[MT], bf[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int grp = wm * (WM / 8) + i;   // group of 8 tile rows
+        const int off = A_KC ? ((grp * 8 + sg) * 128 + ch) : (grp * 1024 + k * 128 + ch);
+        af[i] = *reinterpret_cast<const T*>(a_s + off);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int grp = wn * (WN / 8) + j;
+        const int off = B_KC ? ((grp * 8 + sg) * 128 + ch) : (grp * 1024 + k * 128 + ch);
+        bf[j] = *reinterpret_cast<const T*>(b_s + off);
+      }
+      double as_[MT], bs_[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) { af[i].y *= sgnA; as_[i] = af[i].x + af[i].y; }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { bf[j].y *= sgnB; bs_[j] = bf[j].x + bf[j].y; }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+          dmma884(acc[i][j][2], acc[i][j][3], af[i].y, bf[j].y);
+          dmma884(acc[i][j][4], acc[i][j][5], as_[i], bs_[j]);
+        }
+    }
+    __syncthreads();   // every warp is done with stage s: it may be refilled
+    if (tid == 0 && kt + TMA_STAGES < KT) issue(kt + TMA_STAGES);
+  }
+
+  // epilogue: the thread's accumulator pair of tile (i, j) is C[fragment row gq][fragment columns 2 tq, 2 tq + 1],
+  // i.e. tile row sigma8(gq) and tile columns sigma8(2 tq) = tq, sigma8(2 tq + 1) = 4 + tq of the 8 x 8 block
+  const bool has_beta = (g.beta_r != 0.0 || g.beta_i != 0.0) && g.splits <= 1;
+  const double2 al = g.splits > 1 ? make_double2(1.0, 0.0) : make_double2(g.alpha_r, g.alpha_i);
+  const double2 be = make_double2(g.beta_r, g.beta_i);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int64_t row = m0 + wm * WM + i * 8 + sg;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int64_t cb = n0 + wn * WN + j * 8;
+      T* dst = Cg + row * ldc + cb;
+      double2 v0 = cmul(al, make_double2(acc[i][j][0] - acc[i][j][2], acc[i][j][4] - acc[i][j][0] - acc[i][j][2]));
+      double2 v1 = cmul(al, make_double2(acc[i][j][1] - acc[i][j][3], acc[i][j][5] - acc[i][j][1] - acc[i][j][3]));
+      if (cb + tq < g.N) {
+        if (has_beta) v0 = cadd(v0, cmul(be, dst[tq]));
+        dst[tq] = v0;
+      }
+      if (cb + 4 + tq < g.N) {
+        if (has_beta) v1 = cadd(v1, cmul(be, dst[4 + tq]));
+        dst[4 + tq] = v1;
+      }
+    }
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libtnb does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static std::atomic<void*> cached{nullptr};
+  void* f = cached.load(std::memory_order_acquire);
+  if (!f) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    cudaGetLastError();
+    cached.store(f, std::memory_order_release);
+  }
+  return (EncodeTiledFn)f;
+}
+
+// Tensor map of one complex128 operand viewed as float64 pairs: dims {2 * inner, outer, batch}.
+// kc: global [mn][k] (inner = K, outer = MN, box {8 k, bmn rows});  !kc: global [k][mn] (inner = MN, outer = K,
+// box {8 mn, 8 k rows}).  Returns false when the operand cannot be described (the caller uses the cp.async kernel).
+static bool make_operand_map(CUtensorMap* map, const void* base, bool kc, int64_t MN, int64_t K, int64_t ld, int64_t stride,
+                             int64_t batch, int bmn) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const int64_t inner = kc ? K : MN, outer = kc ? MN : K;
+  if (((uintptr_t)base & 15) != 0 || ld < inner || inner <= 0 || outer <= 0) return false;
+  if (2 * inner >= (1LL << 31) || outer >= (1LL << 31) || batch >= (1LL << 31)) return false;
+  if (batch > 1 && stride <= 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)(2 * inner), (cuuint64_t)outer, (cuuint64_t)batch};
+  const cuuint64_t row_bytes = (cuuint64_t)ld * 16;
+  const cuuint64_t strides[2] = {row_bytes, batch > 1 ? (cuuint64_t)stride * 16 : row_bytes * (cuuint64_t)outer};
+  if (strides[0] >= (1ULL << 40) || strides[1] >= (1ULL << 40)) return false;
+  const cuuint32_t box[3] = {16, (cuuint32_t)(kc ? bmn : 8), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool A_KC, bool B_KC>
+static int launch_gemm_tma(GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int64_t batch, cudaStream_t st) {
+  constexpr size_t smem = (size_t)TMA_STAGES * TMA_STAGE_BYTES + 1024;   // + slack: the base is aligned up to 1 KB
+  auto kern = gemm_tma_kernel<A_KC, B_KC>;
+  static PerDeviceOnce once;
+  if (once.need()) {
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once.done();
+  }
+  g.tiles_m = (int)((g.M + 127) / 128);
+  g.tiles_n = (int)((g.N + 63) / 64);
+  dim3 grid((unsigned)(g.tiles_m * g.tiles_n), (unsigned)batch, (unsigned)(g.splits > 1 ? g.splits : 1));
+  kern<<<grid, 256, smem, st>>>(g, ma, mb);
+  TNB_LAUNCH_CHECK();
+  return 0;
+}
+
+// The TMA path for the full-size complex tile; returns -1 when it does not apply.
+static int try_gemm_tma(GemmArgs& g, bool a_kc, bool b_kc, int64_t batch, cudaStream_t st) {
+  if (batch > 65535) return -1;
+  CUtensorMap ma, mb;
+  if (!make_operand_map(&ma, g.A, a_kc, g.M, g.K, g.lda, g.sA, batch, 128)) return -1;
+  if (!make_operand_map(&mb, g.B, b_kc, g.N, g.K, g.ldb, g.sB, batch, 64)) return -1;
+  if (a_kc && b_kc) return launch_gemm_tma<true, true>(g, ma, mb, batch, st);
+  if (a_kc && !b_kc) return launch_gemm_tma<true, false>(g, ma, mb, batch, st);
+  if (!a_kc && b_kc) return launch_gemm_tma<false, true>(g, ma, mb, batch, st);
+  return launch_gemm_tma<false, false>(g, ma, mb, batch, st);
+}
+
 // C = alpha * sum_z part[z] + beta * C  (deterministic: fixed summation order)
 template <typename T>
 __global__ void splitk_reduce_kernel(const T* part, int splits, int64_t M, int64_t N, T* C, int64_t ldc, double ar,
@@ -365,7 +606,12 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     const int64_t max_by_k = K / (bk * 16);  // keep >= 16 k-steps per split
     const int64_t max_by_ws = (int64_t)(splitk_bytes / ((size_t)M * N * (cplx ? 16 : 8)));
     auto plan = [&](int64_t tiles) {
-      int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;  // aim at ~2 CTAs per SM
+#ifndef TNB_EXP_SPLITK_WAVES_X2
+#define TNB_EXP_SPLITK_WAVES_X2 4   // kernel experiments: target number of CTAs in units of half the SM count
+#endif
+      // aim at ~2 CTAs per SM; the one-wave experiment rounds down so that every CTA is resident at once
+      int64_t want = TNB_EXP_SPLITK_WAVES_X2 == 2 ? (int64_t)sm_count() / tiles
+                                                  : (TNB_EXP_SPLITK_WAVES_X2 * (int64_t)sm_count() / 2 + tiles - 1) / tiles;
       if (want > max_by_k) want = max_by_k;
       if (want > max_by_ws) want = max_by_ws;
       if (want > 64) want = 64;
@@ -393,6 +639,14 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     return 0;
   };
   if (cplx) {
+#ifndef TNB_EXP_NO_TMA
+    if (!small) {
+#else
+    if (false) {   // kernel experiments: cp.async staging everywhere
+#endif
+      const int rt = try_gemm_tma(g, a_kc, b_kc, batch, st);
+      if (rt >= 0) return finish(rt);
+    }
     return finish(small ? dispatch_layout<true, true, true>(g, a_kc, b_kc, batch, st)
                         : dispatch_layout<true, false, true>(g, a_kc, b_kc, batch, st));
   }

@@ -65,25 +65,44 @@ __device__ __forceinline__ typename Pack<MODE>::type apply(typename Pack<MODE>::
   }
 }
 
+// Every thread moves PR_ILP packets per iteration (a CTA covers PR_ILP consecutive runs of 256 packets): the
+// index decomposition of the four packets is interleaved and their loads are all in flight before the first
+// store -- the kernel is latency-bound otherwise (one dependent chain of divisions + one load per thread).
+constexpr int PR_ILP = 4;
 template <int MODE, typename IDX>
 __global__ void __launch_bounds__(256) permute_rows(const typename Pack<MODE>::type* __restrict__ in,
                                                     typename Pack<MODE>::type* __restrict__ out, PermParams p) {
   typedef typename Pack<MODE>::type T;
   const IDX n = (IDX)p.numel;
-  const IDX step = (IDX)gridDim.x * blockDim.x;
-  for (IDX idx = (IDX)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += step) {
-    IDX rem = idx;
-    int64_t off = 0;
+  const IDX step = (IDX)gridDim.x * blockDim.x * PR_ILP;
+  for (IDX base = (IDX)blockIdx.x * blockDim.x * PR_ILP + threadIdx.x; base < n; base += step) {
+    IDX rem[PR_ILP];
+    int64_t off[PR_ILP];
+#pragma unroll
+    for (int u = 0; u < PR_ILP; ++u) {
+      const IDX idx = base + (IDX)u * blockDim.x;
+      rem[u] = idx < n ? idx : (IDX)0;
+      off[u] = 0;
+    }
 #pragma unroll 1
     for (int d = p.rank - 1; d > 0; --d) {
       const IDX s = (IDX)p.oshape[d];
-      const IDX q = rem / s;
-      off += (int64_t)(rem - q * s) * p.istride[d];
-      rem = q;
+      const int64_t is = p.istride[d];
+#pragma unroll
+      for (int u = 0; u < PR_ILP; ++u) {
+        const IDX q = rem[u] / s;
+        off[u] += (int64_t)(rem[u] - q * s) * is;
+        rem[u] = q;
+      }
     }
-    off += (int64_t)rem * p.istride[0];
-    T v = in[off];
-    out[idx] = apply<MODE>(v, p);
+    T v[PR_ILP];
+#pragma unroll
+    for (int u = 0; u < PR_ILP; ++u) v[u] = in[off[u] + (int64_t)rem[u] * p.istride[0]];
+#pragma unroll
+    for (int u = 0; u < PR_ILP; ++u) {
+      const IDX idx = base + (IDX)u * blockDim.x;
+      if (idx < n) out[idx] = apply<MODE>(v[u], p);
+    }
   }
 }
 
@@ -154,7 +173,7 @@ static int launch_permute(const void* in, void* out, PermParams& p, cudaStream_t
     }
   }
   const int threads = 256;
-  int64_t blocks = (p.numel + threads - 1) / threads;
+  int64_t blocks = (p.numel + threads * PR_ILP - 1) / (threads * PR_ILP);
   const int64_t cap = (int64_t)sm_count() * 32;
   if (blocks > cap) blocks = cap;
   if (p.numel < (int64_t)2000000000)
