@@ -6,6 +6,7 @@ tail -6 gpurun_out/r2q_pytest.log
 TNB_LIB_PATH=scratch/exp/libtnb_nopad.so timeout 300 python scratch/jac_time.py > gpurun_out/r2q_jac_nopad.log 2>&1
 timeout 300 python scratch/jac_time.py > gpurun_out/r2q_jac.log 2>&1
 cat gpurun_out/r2q_jac_nopad.log gpurun_out/r2q_jac.log
+timeout 200 python scratch/gemm_shapes.py > gpurun_out/r2q_gemm.log 2>&1; cat gpurun_out/r2q_gemm.log
 timeout 600 python bench.py > gpurun_out/bench_r2q.json 2> gpurun_out/r2q_bench_err.log
 cut -c1-300 gpurun_out/bench_r2q.json; tail -3 gpurun_out/r2q_bench_err.log
 # launch timelines (serialised, cold): one QR 3072x1536, one projection SVD 1024x1536

@@ -136,8 +136,9 @@ gemm_kernel(GemmArgs g) {
     ldc = g.N;
   }
 
-  // complex: 3-multiplication form, three accumulator pairs per 8x8 tile:
-  //   P1 = ar br, P2 = ai bi, P3 = (ar + ai)(br + bi);  re = P1 - P2, im = P3 - P1 - P2
+  // complex: 3-multiplication form, three accumulator pairs per 8x8 tile.  With a = ar + i sA ai, b = br + i sB bi
+  // (sA, sB = -1 for a conjugated operand):
+  //   P1 = ar br, P2 = ai bi, P3 = (ar + sA ai)(br + sB bi);  re = P1 - sA sB P2, im = P3 - P1 - sA sB P2
   double acc[MT][NT][CPLX ? 6 : 2];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
@@ -187,18 +188,20 @@ gemm_kernel(GemmArgs g) {
 #pragma unroll
           for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       } else {
+        // conjugation (sA, sB = -1) enters only through the sums and the epilogue: one FMA per fragment is all
+        // the non-tensor FP64 work of a k-step (it shares the FP64 pipe with the DMMAs)
         double as_[MT], bs_[NT];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) { af[i].y *= sgnA; as_[i] = af[i].x + af[i].y; }
+        for (int i = 0; i < MT; ++i) as_[i] = fma(sgnA, af[i].y, af[i].x);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) { bf[j].y *= sgnB; bs_[j] = bf[j].x + bf[j].y; }
+        for (int j = 0; j < NT; ++j) bs_[j] = fma(sgnB, bf[j].y, bf[j].x);
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
             dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);  // P1 += ar*br
             dmma884(acc[i][j][2], acc[i][j][3], af[i].y, bf[j].y);  // P2 += ai*bi
-            dmma884(acc[i][j][4], acc[i][j][5], as_[i], bs_[j]);    // P3 += (ar+ai)*(br+bi)
+            dmma884(acc[i][j][4], acc[i][j][5], as_[i], bs_[j]);    // P3 += (ar + sA ai)*(br + sB bi)
           }
       }
     }
@@ -231,8 +234,9 @@ gemm_kernel(GemmArgs g) {
         }
       } else {
         const double2 al = make_double2(alpha_r, alpha_i), be = make_double2(g.beta_r, g.beta_i);
-        double2 v0 = cmul(al, make_double2(acc[i][j][0] - acc[i][j][2], acc[i][j][4] - acc[i][j][0] - acc[i][j][2]));
-        double2 v1 = cmul(al, make_double2(acc[i][j][1] - acc[i][j][3], acc[i][j][5] - acc[i][j][1] - acc[i][j][3]));
+        const double p20 = sgnA * sgnB * acc[i][j][2], p21 = sgnA * sgnB * acc[i][j][3];
+        double2 v0 = cmul(al, make_double2(acc[i][j][0] - p20, acc[i][j][4] - acc[i][j][0] - p20));
+        double2 v1 = cmul(al, make_double2(acc[i][j][1] - p21, acc[i][j][5] - acc[i][j][1] - p21));
         if (has_beta) {
           v0 = cadd(v0, cmul(be, dst[0]));
           if (col + 1 < g.N) v1 = cadd(v1, cmul(be, dst[1]));
@@ -391,11 +395,11 @@ __global__ void __launch_bounds__(256) gemm_tma_kernel(GemmArgs g, const __grid_
         const int off = B_KC ? ((grp * 8 + sg) * 128 + ch) : (grp * 1024 + k * 128 + ch);
         bf[j] = *reinterpret_cast<const T*>(b_s + off);
       }
-      double as_[MT], bs_[NT];
+      double as_[MT], bs_[NT];   // conjugation enters through the sums and the epilogue only (see gemm_kernel)
 #pragma unroll
-      for (int i = 0; i < MT; ++i) { af[i].y *= sgnA; as_[i] = af[i].x + af[i].y; }
+      for (int i = 0; i < MT; ++i) as_[i] = fma(sgnA, af[i].y, af[i].x);
 #pragma unroll
-      for (int j = 0; j < NT; ++j) { bf[j].y *= sgnB; bs_[j] = bf[j].x + bf[j].y; }
+      for (int j = 0; j < NT; ++j) bs_[j] = fma(sgnB, bf[j].y, bf[j].x);
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -422,8 +426,9 @@ __global__ void __launch_bounds__(256) gemm_tma_kernel(GemmArgs g, const __grid_
     for (int j = 0; j < NT; ++j) {
       const int64_t cb = n0 + wn * WN + j * 8;
       T* dst = Cg + row * ldc + cb;
-      double2 v0 = cmul(al, make_double2(acc[i][j][0] - acc[i][j][2], acc[i][j][4] - acc[i][j][0] - acc[i][j][2]));
-      double2 v1 = cmul(al, make_double2(acc[i][j][1] - acc[i][j][3], acc[i][j][5] - acc[i][j][1] - acc[i][j][3]));
+      const double p20 = sgnA * sgnB * acc[i][j][2], p21 = sgnA * sgnB * acc[i][j][3];
+      double2 v0 = cmul(al, make_double2(acc[i][j][0] - p20, acc[i][j][4] - acc[i][j][0] - p20));
+      double2 v1 = cmul(al, make_double2(acc[i][j][1] - p21, acc[i][j][5] - acc[i][j][1] - p21));
       if (cb + tq < g.N) {
         if (has_beta) v0 = cadd(v0, cmul(be, dst[tq]));
         dst[tq] = v0;
