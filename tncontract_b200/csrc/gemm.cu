@@ -114,6 +114,8 @@ gemm_kernel(GemmArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sA = reinterpret_cast<T*>(smem_raw);
   T* sB = sA + STAGES * LA::ELEMS;
+  griddep_wait();               // no-ops unless launched with programmatic stream serialization (launch_k)
+  griddep_launch_dependents();
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, tq = lane & 3;  // fragment row / k index
@@ -272,7 +274,7 @@ static int launch_gemm(GemmArgs& g, int64_t batch, cudaStream_t st) {
     h.B = (const char*)g.B + b0 * g.sB * ES;
     h.C = (char*)g.C + b0 * g.sC * ES;
     dim3 grid((unsigned)(g.tiles_m * g.tiles_n), (unsigned)nb, (unsigned)(g.splits > 1 ? g.splits : 1));
-    kern<<<grid, threads, smem, st>>>(h);
+    TNB_CUDA_CHECK(launch_k(kern, grid, dim3(threads), smem, st, h));
     TNB_LAUNCH_CHECK();
   }
   return 0;
@@ -340,6 +342,8 @@ __global__ void __launch_bounds__(256) gemm_tma_kernel(GemmArgs g, const __grid_
     fence_mbar_init();
   }
   __syncthreads();
+  griddep_wait();               // barrier set-up above overlaps the tail of the previous kernel of a chain
+  griddep_launch_dependents();
 
   double acc[MT][NT][6];
 #pragma unroll
@@ -493,7 +497,7 @@ static int launch_gemm_tma(GemmArgs& g, const CUtensorMap& ma, const CUtensorMap
   g.tiles_m = (int)((g.M + 127) / 128);
   g.tiles_n = (int)((g.N + 63) / 64);
   dim3 grid((unsigned)(g.tiles_m * g.tiles_n), (unsigned)batch, (unsigned)(g.splits > 1 ? g.splits : 1));
-  kern<<<grid, 256, smem, st>>>(g, ma, mb);
+  TNB_CUDA_CHECK(launch_k(kern, grid, dim3(256), smem, st, g, ma, mb));
   TNB_LAUNCH_CHECK();
   return 0;
 }
@@ -514,6 +518,8 @@ static int try_gemm_tma(GemmArgs& g, bool a_kc, bool b_kc, int64_t batch, cudaSt
 template <typename T>
 __global__ void splitk_reduce_kernel(const T* part, int splits, int64_t M, int64_t N, T* C, int64_t ldc, double ar,
                                      double ai, double br, double bi) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   const bool has_beta = (br != 0.0 || bi != 0.0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += step) {
@@ -638,8 +644,8 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     if (rc != 0 || g.splits <= 1) return rc;
     int64_t blocks = (M * N + 255) / 256;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
-    if (cplx) splitk_reduce_kernel<double2><<<(unsigned)blocks, 256, 0, st>>>((const double2*)g.part, g.splits, M, N, (double2*)C, ldc, ar, ai, br, bi);
-    else splitk_reduce_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)g.part, g.splits, M, N, (double*)C, ldc, ar, ai, br, bi);
+    if (cplx) TNB_CUDA_CHECK(launch_k(splitk_reduce_kernel<double2>, dim3((unsigned)blocks), dim3(256), 0, st, (const double2*)g.part, g.splits, M, N, (double2*)C, ldc, ar, ai, br, bi));
+    else TNB_CUDA_CHECK(launch_k(splitk_reduce_kernel<double>, dim3((unsigned)blocks), dim3(256), 0, st, (const double*)g.part, g.splits, M, N, (double*)C, ldc, ar, ai, br, bi));
     TNB_LAUNCH_CHECK();
     return 0;
   };

@@ -735,6 +735,8 @@ __global__ void pow2_scale_kernel(const unsigned long long* amax_bits, double* s
 template <typename T>
 __global__ void copy2d_kernel(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows, int64_t cols,
                               const double* scale) {
+  griddep_wait();               // no-ops unless launched with programmatic stream serialization (launch_k)
+  griddep_launch_dependents();
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   const double s = scale ? scale[0] : 1.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += step) {
@@ -902,6 +904,8 @@ __global__ void __launch_bounds__(CI_THREADS) chol_inv_kernel(const T* G, int64_
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   if (tid == 0) s_bad = 0;
+  griddep_wait();
+  griddep_launch_dependents();
   for (int idx = tid; idx < CI_N * CI_N; idx += CI_THREADS) {
     const int i = idx / CI_N, j = idx - i * CI_N;
     T v = N_::zero();
@@ -1041,6 +1045,8 @@ template <typename T>
 __global__ void near_identity_kernel(const T* G, int64_t ldg, int64_t n, T* R, int64_t ldr, T* Rinv, int64_t ldri,
                                      double tol, int* flag) {
   typedef Num<T> N_;
+  griddep_wait();
+  griddep_launch_dependents();
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   bool bad = false;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += step) {
@@ -1126,15 +1132,23 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   auto factorise = [&](const Factor& f, const T* G, int64_t ldg, T* Rinv, int64_t b) -> int {
     ProfScope prof(KC_QR_PANEL, st, (sizeof(T) == 16 ? 4.0 : 1.0) * 2.0 / 3.0 * (double)b * b * b);
     if (f.kind == 0) {
-      kern<<<1, CI_THREADS, ci_smem, st>>>(G, ldg, (int)b, f.Rout, f.ldr, Rinv, LDB, f.rel_floor, f.abs_floor, f.near_tol, flag);
+      TNB_CUDA_CHECK(launch_k(kern, dim3(1), dim3(CI_THREADS), ci_smem, st, G, ldg, (int)b, f.Rout, f.ldr, Rinv, LDB, f.rel_floor,
+                              f.abs_floor, f.near_tol, flag));
     } else {
-      near_identity_kernel<T><<<blocks_for(b * b), 256, 0, st>>>(G, ldg, b, f.Rout, f.ldr, Rinv, LDB, f.near_tol, flag);
+      TNB_CUDA_CHECK(launch_k(near_identity_kernel<T>, dim3(blocks_for(b * b)), dim3(256), 0, st, G, ldg, b, f.Rout, f.ldr, Rinv,
+                              LDB, f.near_tol, flag));
     }
     TNB_LAUNCH_CHECK();
     count_launch();
     return 0;
   };
   int rc;
+#ifdef TNB_EXP_QR_PDL
+  // kernel experiment: the chain S-GEMM -> split-K reduce -> G correction -> Cholesky -> scale GEMM -> copy is a
+  // sequence of short dependent kernels; with programmatic dependent launch each one is scheduled, and runs its
+  // set-up, under the tail of its predecessor
+  PdlScope pdl(true);
+#endif
   // one pass over the panel Qp = Q[:, j0 : j0 + b]:
   //   S (ld lds) <- [Qj, W]^H W;  G = G0 - C^H C in place;  factor;  Bc = [-C R^-1; R^-1];  W <- [Qj, W] Bc
   auto pass = [&](int64_t j0, int64_t b, T* Qp, T* S, int64_t lds, const Factor& f) -> int {
@@ -1171,7 +1185,8 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, kk, 1, 0, Qb, ldq, 0, Bc, LDB, 0, 0, 0, P2, LDB, 0, 1, sk, sk_main, st);
       if (r_) return r_;
     }
-    copy2d_kernel<T><<<blocks_for(m * b), 256, 0, st>>>(P2, LDB, Qp, ldq, m, b, nullptr);
+    TNB_CUDA_CHECK(launch_k(copy2d_kernel<T>, dim3(blocks_for(m * b)), dim3(256), 0, st, (const T*)P2, LDB, Qp, ldq, m, b,
+                            (const double*)nullptr));
     TNB_LAUNCH_CHECK();
     return 0;
   };
