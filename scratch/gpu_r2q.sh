@@ -9,8 +9,11 @@ TNB_LIB_PATH=scratch/exp/libtnb_rotconv.so timeout 300 python scratch/jac_time.p
 cat gpurun_out/r2q_jac_nopad.log gpurun_out/r2q_jac.log gpurun_out/r2q_jac_rotconv.log
 TNB_LIB_PATH=scratch/exp/libtnb_rotconv.so timeout 600 python -m pytest tests -m gpu -q -k "svd or fullsize or batched" > gpurun_out/r2q_pytest_rotconv.log 2>&1; tail -3 gpurun_out/r2q_pytest_rotconv.log
 timeout 200 python scratch/gemm_shapes.py > gpurun_out/r2q_gemm.log 2>&1; cat gpurun_out/r2q_gemm.log
-TNB_LIB_PATH=scratch/exp/libtnb_qrpdl.so timeout 200 python scratch/gemm_shapes.py > gpurun_out/r2q_gemm_qrpdl.log 2>&1; tail -2 gpurun_out/r2q_gemm_qrpdl.log
-TNB_LIB_PATH=scratch/exp/libtnb_qrpdl.so timeout 600 python -m pytest tests -m gpu -q -k "qr or svd or fullsize" > gpurun_out/r2q_pytest_qrpdl.log 2>&1; tail -3 gpurun_out/r2q_pytest_qrpdl.log
+for v in qrpdl qrgrp qrboth; do
+  TNB_LIB_PATH=scratch/exp/libtnb_$v.so timeout 200 python scratch/gemm_shapes.py > gpurun_out/r2q_gemm_$v.log 2>&1; tail -2 gpurun_out/r2q_gemm_$v.log
+  TNB_LIB_PATH=scratch/exp/libtnb_$v.so timeout 600 python -m pytest tests -m gpu -q -k "qr or svd or fullsize" > gpurun_out/r2q_pytest_$v.log 2>&1; tail -3 gpurun_out/r2q_pytest_$v.log
+done
+TNB_LIB_PATH=scratch/exp/libtnb_qrboth.so timeout 600 python bench.py --no-batched --no-cpu-baseline > gpurun_out/bench_r2q_qrboth.json 2> gpurun_out/r2q_bench_qrboth_err.log; cut -c1-200 gpurun_out/bench_r2q_qrboth.json
 timeout 600 python bench.py > gpurun_out/bench_r2q.json 2> gpurun_out/r2q_bench_err.log
 cut -c1-300 gpurun_out/bench_r2q.json; tail -3 gpurun_out/r2q_bench_err.log
 # launch timelines (serialised, cold): one QR 3072x1536, one projection SVD 1024x1536

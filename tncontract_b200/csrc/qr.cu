@@ -1149,40 +1149,41 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   // set-up, under the tail of its predecessor
   PdlScope pdl(true);
 #endif
-  // one pass over the panel Qp = Q[:, j0 : j0 + b]:
-  //   S (ld lds) <- [Qj, W]^H W;  G = G0 - C^H C in place;  factor;  Bc = [-C R^-1; R^-1];  W <- [Qj, W] Bc
-  auto pass = [&](int64_t j0, int64_t b, T* Qp, T* S, int64_t lds, const Factor& f) -> int {
-    const int64_t kk = j0 + b;
-    int r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, kk, b, m, 1, 0, Qb, ldq, 0, Qp, ldq, 0, 0, 0, S, lds, 0, 1, sk, sk_main, st);
+  // one pass over the panel Qp = Q[:, j0 : j0 + b] against the columns Qq = Q[:, q0 : j0] (jl = j0 - q0 of them):
+  //   S (ld lds) <- [Qq, W]^H W;  G = G0 - C^H C in place;  factor;  Bc = [-C R^-1; R^-1];  W <- [Qq, W] Bc
+  auto pass = [&](int64_t q0, int64_t j0, int64_t b, T* Qp, T* S, int64_t lds, const Factor& f) -> int {
+    const int64_t jl = j0 - q0, kk = jl + b;
+    const T* Qq = Qb + q0;
+    int r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, kk, b, m, 1, 0, Qq, ldq, 0, Qp, ldq, 0, 0, 0, S, lds, 0, 1, sk, sk_main, st);
     if (r_) return r_;
-    T* G = S + j0 * lds;
-    T* Ri = Bc + j0 * LDB;
-    const bool fork = overlap && f.kind == 0 && j0 > 0;
+    T* G = S + jl * lds;
+    T* Ri = Bc + jl * LDB;
+    const bool fork = overlap && f.kind == 0 && jl > 0;
     if (fork) {
-      // side stream: W <- W - Qj C in place (C is complete; the Cholesky does not need W)
+      // side stream: W <- W - Qq C in place (C is complete; the Cholesky does not need W)
       TNB_CUDA_CHECK(cudaEventRecord(side.fork, st));
       TNB_CUDA_CHECK(cudaStreamWaitEvent(side.s, side.fork, 0));
     }
-    if (j0 > 0) {
-      r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, b, b, j0, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, sk_main, st);
+    if (jl > 0) {
+      r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, b, b, jl, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, sk_main, st);
       if (r_) return r_;
     }
     factorise(f, G, lds, Ri, b);
     if (fork) {
-      r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, j0, -1, 0, Qb, ldq, 0, S, lds, 0, 1, 0, Qp, ldq, 0, 1, sk_side, sk_side_bytes,
+      r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, jl, -1, 0, Qq, ldq, 0, S, lds, 0, 1, 0, Qp, ldq, 0, 1, sk_side, sk_side_bytes,
                    side.s);
       TNB_CUDA_CHECK(cudaEventRecord(side.join, side.s));
       TNB_CUDA_CHECK(cudaStreamWaitEvent(st, side.join, 0));
       if (r_) return r_;
-      // W <- (W - Qj C) R^-1
+      // W <- (W - Qq C) R^-1
       r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, m, b, b, 1, 0, Qp, ldq, 0, Ri, LDB, 0, 0, 0, P2, LDB, 0, 1, st);
       if (r_) return r_;
     } else {
-      if (j0 > 0) {
-        r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, b, b, -1, 0, S, lds, 0, Ri, LDB, 0, 0, 0, Bc, LDB, 0, 1, st);
+      if (jl > 0) {
+        r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, jl, b, b, -1, 0, S, lds, 0, Ri, LDB, 0, 0, 0, Bc, LDB, 0, 1, st);
         if (r_) return r_;
       }
-      r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, kk, 1, 0, Qb, ldq, 0, Bc, LDB, 0, 0, 0, P2, LDB, 0, 1, sk, sk_main, st);
+      r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, kk, 1, 0, Qq, ldq, 0, Bc, LDB, 0, 0, 0, P2, LDB, 0, 1, sk, sk_main, st);
       if (r_) return r_;
     }
     TNB_CUDA_CHECK(launch_k(copy2d_kernel<T>, dim3(blocks_for(m * b)), dim3(256), 0, st, (const T*)P2, LDB, Qp, ldq, m, b,
@@ -1199,9 +1200,9 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       T* Rjj = Rg + j0 * n + j0;
       copy2d_kernel<T><<<blocks_for(m * bj), 256, 0, st>>>((const T*)A + j0, lda, Qp, ldq, m, bj, sc);
       TNB_LAUNCH_CHECK();
-      rc = pass(j0, bj, Qp, Rj, n, Factor{0, R1, LDB, 1e-10, 0.0, 0.0});
+      rc = pass(0, j0, bj, Qp, Rj, n, Factor{0, R1, LDB, 1e-10, 0.0, 0.0});
       if (rc) return rc;
-      rc = pass(j0, bj, Qp, Sb, LDB, Factor{0, R2, LDB, 0.0, 0.25, 1e-8});
+      rc = pass(0, j0, bj, Qp, Sb, LDB, Factor{0, R2, LDB, 0.0, 0.25, 1e-8});
       if (rc) return rc;
       if (j0 > 0) {  // R[:j0, J] = C1 + C2 R1
         rc = gemm(dtype, TNB_OP_N, TNB_OP_N, j0, bj, bj, 1, 0, Sb, LDB, 0, R1, LDB, 0, 1, 0, Rj, n, 0, 1, st);
@@ -1221,12 +1222,26 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       const int64_t bg = (k - g0 < QR_GB) ? (k - g0) : QR_GB;
       copy2d_kernel<T><<<blocks_for(m * bg), 256, 0, st>>>((const T*)A + g0, lda, Qb + g0, ldq, m, bg, sc);
       TNB_LAUNCH_CHECK();
-      for (int64_t j0 = g0; j0 < g0 + bg; j0 += QR_CB) {
-        const int64_t bj = (g0 + bg - j0 < QR_CB) ? (g0 + bg - j0) : QR_CB;
-        rc = pass(j0, bj, Qb + j0, Rg + j0, n, Factor{0, Rg + j0 * n + j0, n, 1e-10, 0.0, 0.0});
+#ifdef TNB_EXP_QR_GROUPPROJ
+      // kernel experiment: the group is first projected against all earlier groups as a whole (two GEMMs with
+      // N = 256 instead of 2 x 4 with N = 64), the couplings landing in R[:g0, G]; the 64-column blocks then only
+      // meet the earlier blocks of their own group
+      const int64_t q0 = g0;
+      if (g0 > 0) {
+        rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, g0, bg, m, 1, 0, Qb, ldq, 0, Qb + g0, ldq, 0, 0, 0, Rg + g0, n, 0, 1, sk, sk_main, st);
+        if (rc) return rc;
+        rc = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, bg, g0, -1, 0, Qb, ldq, 0, Rg + g0, n, 0, 1, 0, Qb + g0, ldq, 0, 1, sk, sk_main, st);
         if (rc) return rc;
       }
-      rc = pass(g0, bg, Qb + g0, Sb, LDB, Factor{1, R2, LDB, 0.0, 0.0, 1e-8});
+#else
+      const int64_t q0 = 0;
+#endif
+      for (int64_t j0 = g0; j0 < g0 + bg; j0 += QR_CB) {
+        const int64_t bj = (g0 + bg - j0 < QR_CB) ? (g0 + bg - j0) : QR_CB;
+        rc = pass(q0, j0, bj, Qb + j0, Rg + q0 * n + j0, n, Factor{0, Rg + j0 * n + j0, n, 1e-10, 0.0, 0.0});
+        if (rc) return rc;
+      }
+      rc = pass(0, g0, bg, Qb + g0, Sb, LDB, Factor{1, R2, LDB, 0.0, 0.0, 1e-8});
       if (rc) return rc;
       // R[G, G] = R2 R1g,  R[:g0, G] = C1 + C2 R1g   (R1g = the group's first-pass factor, now in R[G, G])
       T* Rgg = Rg + g0 * n + g0;
