@@ -113,6 +113,13 @@ int tnb_gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K,
              const void* B, int64_t ldb, int64_t strideB,
              const double* beta /*[2]*/, void* C, int64_t ldc, int64_t strideC,
              int64_t batch, void* stream);
+/* The same product with caller-provided scratch for split-K: a product with few C tiles and a long K
+ * (Gram-like shapes: the Q^H W products under np.linalg.qr, tensor.py:1044) is cut along K over
+ * grid.z and reduced in a second, deterministic kernel.  Any ws_bytes >= 0 is valid (more scratch
+ * allows more splits; M*N*sizeof(elem) per split); batch must be 1 for the split to apply. */
+int tnb_gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K,
+                const double* alpha /*[2]*/, const void* A, int64_t lda, const void* B, int64_t ldb,
+                const double* beta /*[2]*/, void* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- tensordot: np.tensordot(a, b, (axes_a, axes_b)) (tensor.py:735) -------
  * out is contiguous with shape free(a) ++ free(b).  conj flags fold

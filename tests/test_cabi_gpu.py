@@ -116,6 +116,36 @@ def test_gemm_all_ops(cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+def test_gemm_split_k(cplx):
+    """tnb_gemm_ws: Gram-like shapes (few C tiles, long K) cut along K over grid.z and reduced by the second kernel --
+    the products under the Gram-Schmidt QR; all four operand layouts, conjugation, alpha / beta, K not a multiple of
+    the split, and a scratch too small for any split (plain path)."""
+    torch, _lib, dv = _mods()
+    lib = _lib.load()
+    rng = np.random.default_rng(13)
+    code, tdt = (1, torch.complex128) if cplx else (0, torch.float64)
+    op = lambda x, o: x if o == 0 else x.T if o == 1 else x.conj().T if o == 2 else x.conj()
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    for M, N, K in [(200, 64, 3000), (1100, 64, 3072), (256, 256, 2050), (64, 64, 1500)]:
+        for oa, ob in [(2, 0), (0, 0), (1, 3), (3, 2)]:
+            As = rnd(rng, (M, K) if oa in (0, 3) else (K, M), cplx)
+            Bs = rnd(rng, (K, N) if ob in (0, 3) else (N, K), cplx)
+            C0 = rnd(rng, (M, N), cplx)
+            alpha = (-1.0 + 0.25j) if cplx else -1.0
+            beta = (1.0 + 0j) if cplx else 1.0
+            A, B = torch.from_numpy(As).cuda(), torch.from_numpy(Bs).cuda()
+            ref = alpha * op(As, oa) @ op(Bs, ob) + beta * C0
+            for nbytes in (ws.numel(), 1024):
+                C = torch.from_numpy(C0.astype(As.dtype)).cuda()
+                al = (ctypes.c_double * 2)(np.real(alpha), np.imag(alpha))
+                be = (ctypes.c_double * 2)(np.real(beta), np.imag(beta))
+                rc = lib.tnb_gemm_ws(code, oa, ob, M, N, K, al, A.data_ptr(), As.shape[1], B.data_ptr(), Bs.shape[1], be,
+                                     C.data_ptr(), N, ws.data_ptr(), nbytes, dv.stream_ptr())
+                assert rc == 0
+                assert rel(C.cpu().numpy(), ref) < TOL, (M, N, K, oa, ob, nbytes)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_tensordot_layouts(cplx):
     torch, _lib, dv = _mods()
     rng = np.random.default_rng(2)

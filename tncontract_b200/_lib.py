@@ -54,6 +54,8 @@ SIGNATURES = {
     "tnb_fill_uniform": (_c.c_int, [_vp, _i64, _c.c_ulonglong, _c.c_ulonglong, _vp]),
     "tnb_gemm": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _i64, _i64, _i64, _pdbl, _vp, _i64, _i64, _vp, _i64, _i64,
                             _pdbl, _vp, _i64, _i64, _i64, _vp]),
+    "tnb_gemm_ws": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _i64, _i64, _i64, _pdbl, _vp, _i64, _vp, _i64, _pdbl, _vp, _i64,
+                               _vp, _sz, _vp]),
     "tnb_tensordot_workspace": (_sz, [_pd, _pd, _c.c_int, _pi32, _pi32]),
     "tnb_tensordot": (_c.c_int, [_pd, _pd, _c.c_int, _pi32, _pi32, _c.c_int, _c.c_int, _vp, _vp, _sz, _vp]),
     "tnb_mps_mpo_site": (_c.c_int, [_pd, _pd, _vp, _vp]),

@@ -628,7 +628,12 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
       if (want > 64) want = 64;
       return want < 1 ? (int64_t)1 : want;
     };
-    if (small && M > 64 && N > (cplx ? 32 : 64) && big_tiles * plan(big_tiles) * 5 >= (int64_t)sm_count() * 4) small = false;
+#ifdef TNB_EXP_SKINNY_SMALL
+    const bool keep_small = N <= (cplx ? 64 : 128);   // kernel experiment: one tile column -> small tiles
+#else
+    const bool keep_small = false;
+#endif
+    if (small && !keep_small && M > 64 && N > (cplx ? 32 : 64) && big_tiles * plan(big_tiles) * 5 >= (int64_t)sm_count() * 4) small = false;
     const int64_t bm = small ? 64 : 128, bn = cplx ? (small ? 32 : 64) : (small ? 64 : 128);
     const int64_t tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
     const int64_t want = plan(tiles);
@@ -679,4 +684,13 @@ extern "C" int tnb_gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64
   if (opA < 0 || opA > 3 || opB < 0 || opB > 3) return TNB_E_ARG;
   return tnb::gemm(dtype, opA, opB, M, N, K, alpha[0], alpha[1], A, lda, strideA, B, ldb, strideB, beta[0], beta[1],
                    C, ldc, strideC, batch, (cudaStream_t)stream);
+}
+
+extern "C" int tnb_gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, const double* alpha,
+                           const void* A, int64_t lda, const void* B, int64_t ldb, const double* beta, void* C,
+                           int64_t ldc, void* ws, size_t ws_bytes, void* stream) {
+  if (!alpha || !beta) return TNB_E_ARG;
+  if (opA < 0 || opA > 3 || opB < 0 || opB > 3) return TNB_E_ARG;
+  return tnb::gemm_ws(dtype, opA, opB, M, N, K, alpha[0], alpha[1], A, lda, 0, B, ldb, 0, beta[0], beta[1], C, ldc, 0, 1,
+                      ws_bytes ? ws : nullptr, ws_bytes, (cudaStream_t)stream);
 }
