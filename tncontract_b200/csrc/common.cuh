@@ -197,9 +197,12 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
-// Host side of programmatic dependent launch for kernel chains (qr.cu): inside a PdlScope every launch made
-// through launch_k() carries the programmatic-stream-serialization attribute.  Only kernels that execute
-// griddep_wait() before their first global-memory access may be launched this way.
+// Host side of programmatic dependent launch for kernel chains: inside a PdlScope every launch made through
+// launch_k() carries the programmatic-stream-serialization attribute.  Only kernels that execute griddep_wait()
+// before their first global-memory access may be launched this way (the GEMM, split-K reduce, Cholesky and copy
+// kernels do).  Measured on the Gram-Schmidt QR chain (3072 x 1536 complex128): 7.40 ms with the scope against
+// 6.71 without -- the early-scheduled CTAs of the next short kernel take SM slots from the side-stream GEMM -- so
+// no caller opens a scope today; the Jacobi rounds carry the attribute themselves (svd.cu launch_round).
 extern thread_local int g_pdl;
 struct PdlScope {
   bool on;

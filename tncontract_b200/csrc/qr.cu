@@ -1143,12 +1143,6 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     return 0;
   };
   int rc;
-#ifdef TNB_EXP_QR_PDL
-  // kernel experiment: the chain S-GEMM -> split-K reduce -> G correction -> Cholesky -> scale GEMM -> copy is a
-  // sequence of short dependent kernels; with programmatic dependent launch each one is scheduled, and runs its
-  // set-up, under the tail of its predecessor
-  PdlScope pdl(true);
-#endif
   // one pass over the panel Qp = Q[:, j0 : j0 + b] against the columns Qq = Q[:, q0 : j0] (jl = j0 - q0 of them):
   //   S (ld lds) <- [Qq, W]^H W;  G = G0 - C^H C in place;  factor;  Bc = [-C R^-1; R^-1];  W <- [Qq, W] Bc
   auto pass = [&](int64_t q0, int64_t j0, int64_t b, T* Qp, T* S, int64_t lds, const Factor& f) -> int {

@@ -269,16 +269,8 @@ struct RotCtx {
 
 template <typename T, typename GT>
 __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename Num<GT>::real_t (*s_rc)[JP / 2],
-                                               GT (*s_rsp)[JP / 2], double (*s_rc64)[JP / 2], T (*s_rsp64)[JP / 2],
-                                               const RotCtx& cx, cg::cluster_group& cluster,
+                                               GT (*s_rsp)[JP / 2], const RotCtx& cx, cg::cluster_group& cluster,
                                                unsigned& state, int warp, int lane) {
-#ifdef TNB_EXP_ROTCONV
-  // kernel experiment: the rotation warp re-normalises each single-precision rotation to double precision ONCE
-  // (s_rc64 / s_rsp64) instead of every W task doing it for itself (16 x per rotation with four CTAs)
-  constexpr bool CONV = sizeof(GT) != sizeof(T);
-#else
-  constexpr bool CONV = false;
-#endif
   typedef Num<T> N_;
   typedef Num<GT> NG;
   constexpr int ROTW = JT / 32 - 1;
@@ -288,11 +280,6 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
     const Rot<GT> r = make_rot<GT>(G, cx.rr[0][lane][0], cx.rr[0][lane][1], cx.tol2, state);
     s_rc[0][lane] = r.c;
     s_rsp[0][lane] = r.sp;
-    if constexpr (CONV) {
-      const Rot<T> r64 = load_rot<T, GT>(s_rc[0], s_rsp[0], lane);   // reads back this lane's own entries
-      s_rc64[0][lane] = r64.c;
-      s_rsp64[0][lane] = r64.sp;
-    }
   }
   // the rotation warp fetches its table word one step ahead (it does not depend on the data)
   unsigned nx_ahead = (warp == ROTW && lane < JP / 2 && nsteps > 1) ? cx.nxt[0][lane] : 0u;
@@ -323,11 +310,6 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
         const Rot<GT> r = make_rot_vals<GT>(NG::real(al), NG::real(be), ga, cx.tol2, state);
         s_rc[cur ^ 1][lane] = r.c;
         s_rsp[cur ^ 1][lane] = r.sp;
-        if constexpr (CONV) {
-          const Rot<T> r64 = load_rot<T, GT>(s_rc[cur ^ 1], s_rsp[cur ^ 1], lane);
-          s_rc64[cur ^ 1][lane] = r64.c;
-          s_rsp64[cur ^ 1][lane] = r64.sp;
-        }
       }
       JSTAMP(2 + 4 * step, lane == 0);
     } else if (cx.g0 >= 0) {
@@ -364,9 +346,7 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
       for (int task = cx.wi * 32 + lane; task < cx.w_tasks; task += cx.nw * 32) {
         const int row = cx.w_first + (task >> 4), wb = task & 15;
         const int pb = cx.rr[step][wb][0], qb = cx.rr[step][wb][1];
-        Rot<T> Rb;
-        if constexpr (CONV) { Rb.c = s_rc64[cur][wb]; Rb.sp = s_rsp64[cur][wb]; }
-        else Rb = load_rot<T, GT>(s_rc[cur], s_rsp[cur], wb);
+        const Rot<T> Rb = load_rot<T, GT>(s_rc[cur], s_rsp[cur], wb);
         const T msb = N_::sub(N_::zero(), N_::conj(Rb.sp));
         const T w0 = Wc[row * JWP + pb], w1 = Wc[row * JWP + qb];
         const T v0 = rot_mix(Rb.c, w0, msb, w1), v1 = rot_mix(Rb.c, w1, Rb.sp, w0);
@@ -667,8 +647,6 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   cx.tol2 = a.tol * a.tol;
   unsigned state = 0;
   __shared__ double s_rc[2][JP / 2];
-  __shared__ double s_rc64[2][JP / 2];   // the rotations as the matrix sees them (TNB_EXP_ROTCONV)
-  __shared__ T s_rsp64[2][JP / 2];
   __shared__ T s_rsp[2][JP / 2];
 #ifndef TNB_EXP_SKIP_EIGEN
   bool use32 = false;
@@ -695,9 +673,9 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     }
     __syncthreads();
     rotation_phase<T, GT>(G32, JP * JGG, W, reinterpret_cast<float (*)[JP / 2]>(s_rc),
-                          reinterpret_cast<GT (*)[JP / 2]>(s_rsp), s_rc64, s_rsp64, cx, cluster, state, warp, lane);
+                          reinterpret_cast<GT (*)[JP / 2]>(s_rsp), cx, cluster, state, warp, lane);
   } else {
-    rotation_phase<T, T>(G, JP * JGP, W, s_rc, s_rsp, s_rc64, s_rsp64, cx, cluster, state, warp, lane);
+    rotation_phase<T, T>(G, JP * JGP, W, s_rc, s_rsp, cx, cluster, state, warp, lane);
   }
   W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
 #endif
