@@ -616,27 +616,21 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     const int64_t bk = cplx ? 8 : 16;
     const int64_t max_by_k = K / (bk * 16);  // keep >= 16 k-steps per split
     const int64_t max_by_ws = (int64_t)(splitk_bytes / ((size_t)M * N * (cplx ? 16 : 8)));
-    auto plan = [&](int64_t tiles) {
-#ifndef TNB_EXP_SPLITK_WAVES_X2
-#define TNB_EXP_SPLITK_WAVES_X2 4   // kernel experiments: target number of CTAs in units of half the SM count
-#endif
-      // aim at ~2 CTAs per SM; the one-wave experiment rounds down so that every CTA is resident at once
-      int64_t want = TNB_EXP_SPLITK_WAVES_X2 == 2 ? (int64_t)sm_count() / tiles
-                                                  : (TNB_EXP_SPLITK_WAVES_X2 * (int64_t)sm_count() / 2 + tiles - 1) / tiles;
+    // CTAs that are resident at once: the full-size tile needs 145 KB / 244 registers (one CTA per SM), the small
+    // one fits twice.  The split aims at ONE full wave, rounded down (a few CTAs more than a wave cost a whole extra
+    // wave: measured 89 -> 67 us on the 1152 x 64 x 3072 product of the QR, 357 -> 271 us on 1536 x 256 x 3072)
+    auto plan = [&](int64_t tiles, bool small_tile) {
+      const int64_t capacity = (int64_t)sm_count() * (small_tile ? 2 : 1);
+      int64_t want = capacity / tiles;
       if (want > max_by_k) want = max_by_k;
       if (want > max_by_ws) want = max_by_ws;
       if (want > 64) want = 64;
       return want < 1 ? (int64_t)1 : want;
     };
-#ifdef TNB_EXP_SKINNY_SMALL
-    const bool keep_small = N <= (cplx ? 64 : 128);   // kernel experiment: one tile column -> small tiles
-#else
-    const bool keep_small = false;
-#endif
-    if (small && !keep_small && M > 64 && N > (cplx ? 32 : 64) && big_tiles * plan(big_tiles) * 5 >= (int64_t)sm_count() * 4) small = false;
+    if (small && M > 64 && N > (cplx ? 32 : 64) && big_tiles * plan(big_tiles, false) * 5 >= (int64_t)sm_count() * 4) small = false;
     const int64_t bm = small ? 64 : 128, bn = cplx ? (small ? 32 : 64) : (small ? 64 : 128);
     const int64_t tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
-    const int64_t want = plan(tiles);
+    const int64_t want = plan(tiles, small);
     if (want >= 2) {
       int64_t kps = (K + want - 1) / want;
       kps = ((kps + bk - 1) / bk) * bk;

@@ -744,6 +744,77 @@ __global__ void copy2d_kernel(const T* src, int64_t lds, T* dst, int64_t ldd, in
     dst[r * ldd + c] = Num<T>::scale(src[r * lds + c], s);
   }
 }
+// W (m x b, ld ldw) <- W * Rinv (b x b upper triangular, ld ldr), in place, b <= 64: the last step of a first pass
+// of qr_bcgs2.  As a GEMM this is m x 64 x 64 -- eight k-steps, so pipeline fill, epilogue and the copy back from a
+// second buffer cost more than the product (19 + 4 us measured); here one CTA of four warps owns 32 rows: the rows
+// and Rinv are staged once in shared memory (pitches as the GEMM's K- and MN-contiguous tiles: conflict-free DMMA
+// fragments), every warp forms 8 rows x 64 columns on DMMA -- only the k <= n half of the triangular factor -- and
+// writes them back over its own rows.
+constexpr int PS_ROWS = 32, PS_N = 64, PS_WP = PS_N + 4;
+template <typename T> struct PsPitch { static constexpr int RP = sizeof(T) == 16 ? PS_N + 2 : PS_N + 4; };   // pitch of Rinv[k][n]
+template <typename T>
+__global__ void __launch_bounds__(128) panel_scale_kernel(T* W, int64_t ldw, int64_t m, int b, const T* Rinv, int64_t ldr) {
+  typedef Num<T> N_;
+  constexpr bool CPLX = sizeof(T) == 16;
+  constexpr int PS_RP = PsPitch<T>::RP;
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  T* Ws = reinterpret_cast<T*>(ps_smem);      // [PS_ROWS][PS_WP]  rows of W, k contiguous
+  T* Rs = Ws + PS_ROWS * PS_WP;               // [PS_N][PS_RP]     Rinv[k][n], n contiguous; zero outside the triangle / b
+  griddep_wait();
+  griddep_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int64_t r0 = (int64_t)blockIdx.x * PS_ROWS;
+  for (int idx = tid; idx < PS_N * PS_N; idx += 128) {
+    const int k = idx / PS_N, n = idx - k * PS_N;
+    Rs[k * PS_RP + n] = (k <= n && n < b) ? Rinv[(int64_t)k * ldr + n] : N_::zero();
+  }
+  for (int idx = tid; idx < PS_ROWS * PS_N; idx += 128) {
+    const int r = idx / PS_N, k = idx - r * PS_N;
+    Ws[r * PS_WP + k] = (r0 + r < m && k < b) ? W[(r0 + r) * ldw + k] : N_::zero();
+  }
+  __syncthreads();
+  constexpr int NACC = CPLX ? 6 : 2;
+  double acc[PS_N / 8][NACC];
+#pragma unroll
+  for (int j = 0; j < PS_N / 8; ++j)
+#pragma unroll
+    for (int r = 0; r < NACC; ++r) acc[j][r] = 0.0;
+  const T* wrow = Ws + (warp * 8 + gq) * PS_WP + tq;
+#pragma unroll
+  for (int k0 = 0; k0 < PS_N; k0 += 4) {
+    const T av = wrow[k0];
+    double as_ = 0.0;
+    if constexpr (CPLX) as_ = av.x + av.y;
+#pragma unroll
+    for (int j = 0; j < PS_N / 8; ++j) {
+      if (k0 > 8 * j + 7) continue;          // Rinv[k][n] = 0 for k > n (resolved at compile time: both loops unrolled)
+      const T bv = Rs[(k0 + tq) * PS_RP + j * 8 + gq];
+      if constexpr (CPLX) {
+        dmma884(acc[j][0], acc[j][1], av.x, bv.x);
+        dmma884(acc[j][2], acc[j][3], av.y, bv.y);
+        dmma884(acc[j][4], acc[j][5], as_, bv.x + bv.y);
+      } else {
+        dmma884(acc[j][0], acc[j][1], av, bv);
+      }
+    }
+  }
+  const int64_t row = r0 + warp * 8 + gq;
+  if (row < m) {
+#pragma unroll
+    for (int j = 0; j < PS_N / 8; ++j) {
+      const int col = j * 8 + 2 * tq;
+      T v0, v1;
+      if constexpr (CPLX) {
+        v0 = make_double2(acc[j][0] - acc[j][2], acc[j][4] - acc[j][0] - acc[j][2]);
+        v1 = make_double2(acc[j][1] - acc[j][3], acc[j][5] - acc[j][1] - acc[j][3]);
+      } else {
+        v0 = acc[j][0]; v1 = acc[j][1];
+      }
+      if (col < b) W[row * ldw + col] = v0;
+      if (col + 1 < b) W[row * ldw + col + 1] = v1;
+    }
+  }
+}
 // R = triu(W[0:k, 0:n]) (times unscale[1] when given)
 template <typename T>
 __global__ void extract_r_kernel(const T* W, int64_t ldw, T* R, int64_t k, int64_t n, const double* unscale) {
@@ -1122,9 +1193,11 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   TNB_CUDA_CHECK(cudaMemsetAsync(Rg, 0, (size_t)k * n * sizeof(T), st));
   auto kern = chol_inv_kernel<T>;
   constexpr size_t ci_smem = (size_t)3 * CI_N * CI_P * sizeof(T);
+  constexpr size_t ps_smem_bytes = (size_t)(PS_ROWS * PS_WP + PS_N * PsPitch<T>::RP) * sizeof(T);
   static PerDeviceOnce once;
   if (once.need()) {
     TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ci_smem));
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(panel_scale_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem_bytes));
     once.done();
   }
   // the small factor of a pass: G (ld ldg) -> Rout (ld ldr), R^-1 -> Rinv (ld LDB)
@@ -1169,7 +1242,13 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       TNB_CUDA_CHECK(cudaEventRecord(side.join, side.s));
       TNB_CUDA_CHECK(cudaStreamWaitEvent(st, side.join, 0));
       if (r_) return r_;
-      // W <- (W - Qq C) R^-1
+      // W <- (W - Qq C) R^-1, in place
+      if (b <= PS_N) {
+        TNB_CUDA_CHECK(launch_k(panel_scale_kernel<T>, dim3((unsigned)((m + PS_ROWS - 1) / PS_ROWS)), dim3(128), ps_smem_bytes, st,
+                                Qp, ldq, m, (int)b, (const T*)Ri, LDB));
+        TNB_LAUNCH_CHECK();
+        return 0;
+      }
       r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, m, b, b, 1, 0, Qp, ldq, 0, Ri, LDB, 0, 0, 0, P2, LDB, 0, 1, st);
       if (r_) return r_;
     } else {
