@@ -746,73 +746,71 @@ __global__ void copy2d_kernel(const T* src, int64_t lds, T* dst, int64_t ldd, in
 }
 // W (m x b, ld ldw) <- W * Rinv (b x b upper triangular, ld ldr), in place, b <= 64: the last step of a first pass
 // of qr_bcgs2.  As a GEMM this is m x 64 x 64 -- eight k-steps, so pipeline fill, epilogue and the copy back from a
-// second buffer cost more than the product (19 + 4 us measured); here one CTA of four warps owns 32 rows: the rows
-// and Rinv are staged once in shared memory (pitches as the GEMM's K- and MN-contiguous tiles: conflict-free DMMA
-// fragments), every warp forms 8 rows x 64 columns on DMMA -- only the k <= n half of the triangular factor -- and
-// writes them back over its own rows.
+// second buffer cost more than the product (19 + 4 us measured).  Here one CTA of eight warps owns 32 rows, staged
+// once in shared memory (pitch as the GEMM's K-contiguous tile: conflict-free DMMA fragments); warp j forms the
+// eight columns 8j .. 8j + 7 of all 32 rows on DMMA and keeps ITS columns of Rinv -- only the k <= 8j + 7 part of
+// the triangular factor -- as B fragments in registers, loaded once from global memory; the results go back over
+// the CTA's own rows.
 constexpr int PS_ROWS = 32, PS_N = 64, PS_WP = PS_N + 4;
-template <typename T> struct PsPitch { static constexpr int RP = sizeof(T) == 16 ? PS_N + 2 : PS_N + 4; };   // pitch of Rinv[k][n]
 template <typename T>
-__global__ void __launch_bounds__(128) panel_scale_kernel(T* W, int64_t ldw, int64_t m, int b, const T* Rinv, int64_t ldr) {
+__global__ void __launch_bounds__(256) panel_scale_kernel(T* W, int64_t ldw, int64_t m, int b, const T* Rinv, int64_t ldr) {
   typedef Num<T> N_;
   constexpr bool CPLX = sizeof(T) == 16;
-  constexpr int PS_RP = PsPitch<T>::RP;
-  extern __shared__ __align__(16) unsigned char ps_smem[];
-  T* Ws = reinterpret_cast<T*>(ps_smem);      // [PS_ROWS][PS_WP]  rows of W, k contiguous
-  T* Rs = Ws + PS_ROWS * PS_WP;               // [PS_N][PS_RP]     Rinv[k][n], n contiguous; zero outside the triangle / b
+  __shared__ __align__(16) T Ws[PS_ROWS * PS_WP];   // rows of W, k contiguous
   griddep_wait();
   griddep_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   const int64_t r0 = (int64_t)blockIdx.x * PS_ROWS;
-  for (int idx = tid; idx < PS_N * PS_N; idx += 128) {
-    const int k = idx / PS_N, n = idx - k * PS_N;
-    Rs[k * PS_RP + n] = (k <= n && n < b) ? Rinv[(int64_t)k * ldr + n] : N_::zero();
+  // B fragments of this warp's column tile: Rinv[k = k0 + tq][n = 8 warp + gq], zero outside the triangle / b
+  T bf[PS_N / 4];
+#pragma unroll
+  for (int ks = 0; ks < PS_N / 4; ++ks) {
+    const int kk = ks * 4 + tq, n = warp * 8 + gq;
+    bf[ks] = (ks * 4 <= warp * 8 + 7 && kk <= n && n < b) ? Rinv[(int64_t)kk * ldr + n] : N_::zero();
   }
-  for (int idx = tid; idx < PS_ROWS * PS_N; idx += 128) {
-    const int r = idx / PS_N, k = idx - r * PS_N;
-    Ws[r * PS_WP + k] = (r0 + r < m && k < b) ? W[(r0 + r) * ldw + k] : N_::zero();
+  for (int idx = tid; idx < PS_ROWS * PS_N; idx += 256) {
+    const int r = idx / PS_N, kk = idx - r * PS_N;
+    Ws[r * PS_WP + kk] = (r0 + r < m && kk < b) ? W[(r0 + r) * ldw + kk] : N_::zero();
   }
   __syncthreads();
   constexpr int NACC = CPLX ? 6 : 2;
-  double acc[PS_N / 8][NACC];
+  double acc[PS_ROWS / 8][NACC];
 #pragma unroll
-  for (int j = 0; j < PS_N / 8; ++j)
+  for (int i = 0; i < PS_ROWS / 8; ++i)
 #pragma unroll
-    for (int r = 0; r < NACC; ++r) acc[j][r] = 0.0;
-  const T* wrow = Ws + (warp * 8 + gq) * PS_WP + tq;
+    for (int r = 0; r < NACC; ++r) acc[i][r] = 0.0;
 #pragma unroll
-  for (int k0 = 0; k0 < PS_N; k0 += 4) {
-    const T av = wrow[k0];
-    double as_ = 0.0;
-    if constexpr (CPLX) as_ = av.x + av.y;
+  for (int ks = 0; ks < PS_N / 4; ++ks) {
+    if (ks * 4 > warp * 8 + 7) break;        // Rinv[k][n] = 0 for k > n (uniform over the warp)
+    const T bv = bf[ks];
+    double bs = 0.0;
+    if constexpr (CPLX) bs = bv.x + bv.y;
 #pragma unroll
-    for (int j = 0; j < PS_N / 8; ++j) {
-      if (k0 > 8 * j + 7) continue;          // Rinv[k][n] = 0 for k > n (resolved at compile time: both loops unrolled)
-      const T bv = Rs[(k0 + tq) * PS_RP + j * 8 + gq];
+    for (int i = 0; i < PS_ROWS / 8; ++i) {
+      const T av = Ws[(i * 8 + gq) * PS_WP + ks * 4 + tq];
       if constexpr (CPLX) {
-        dmma884(acc[j][0], acc[j][1], av.x, bv.x);
-        dmma884(acc[j][2], acc[j][3], av.y, bv.y);
-        dmma884(acc[j][4], acc[j][5], as_, bv.x + bv.y);
+        dmma884(acc[i][0], acc[i][1], av.x, bv.x);
+        dmma884(acc[i][2], acc[i][3], av.y, bv.y);
+        dmma884(acc[i][4], acc[i][5], av.x + av.y, bs);
       } else {
-        dmma884(acc[j][0], acc[j][1], av, bv);
+        dmma884(acc[i][0], acc[i][1], av, bv);
       }
     }
   }
-  const int64_t row = r0 + warp * 8 + gq;
-  if (row < m) {
+  const int col = warp * 8 + 2 * tq;
 #pragma unroll
-    for (int j = 0; j < PS_N / 8; ++j) {
-      const int col = j * 8 + 2 * tq;
-      T v0, v1;
-      if constexpr (CPLX) {
-        v0 = make_double2(acc[j][0] - acc[j][2], acc[j][4] - acc[j][0] - acc[j][2]);
-        v1 = make_double2(acc[j][1] - acc[j][3], acc[j][5] - acc[j][1] - acc[j][3]);
-      } else {
-        v0 = acc[j][0]; v1 = acc[j][1];
-      }
-      if (col < b) W[row * ldw + col] = v0;
-      if (col + 1 < b) W[row * ldw + col + 1] = v1;
+  for (int i = 0; i < PS_ROWS / 8; ++i) {
+    const int64_t row = r0 + i * 8 + gq;
+    if (row >= m) continue;
+    T v0, v1;
+    if constexpr (CPLX) {
+      v0 = make_double2(acc[i][0] - acc[i][2], acc[i][4] - acc[i][0] - acc[i][2]);
+      v1 = make_double2(acc[i][1] - acc[i][3], acc[i][5] - acc[i][1] - acc[i][3]);
+    } else {
+      v0 = acc[i][0]; v1 = acc[i][1];
     }
+    if (col < b) W[row * ldw + col] = v0;
+    if (col + 1 < b) W[row * ldw + col + 1] = v1;
   }
 }
 // R = triu(W[0:k, 0:n]) (times unscale[1] when given)
@@ -954,6 +952,7 @@ static int launch_panel(QrPanelArgs& a, cudaStream_t st) {
 // numerically dependent columns), raises a device flag; the caller then runs the Householder path on the
 // untouched A.
 // ---------------------------------------------------------------------------------------------------
+template <typename T> struct CPLX_CI { static constexpr bool value = sizeof(T) == 16; };
 constexpr int CI_N = QR_CB;       // matrix order handled by chol_inv_kernel
 constexpr int CI_P = CI_N + 1;    // shared-memory pitch
 constexpr int CI_THREADS = 512;
@@ -1013,21 +1012,60 @@ __global__ void __launch_bounds__(CI_THREADS) chol_inv_kernel(const T* G, int64_
     }
   }
   if (tid < CI_N) diag0[tid] = N_::real(A[tid * CI_P + tid]);
-  // right-looking Cholesky on the upper triangle, rows kept unscaled (Schur complements); thread owns
-  // column k and rows i0 .. i0 + 7
+  // Right-looking Cholesky on the upper triangle, rows kept unscaled (Schur complements: U, with R = D^-1/2 U),
+  // blocked by 8 rows.  The 8 pivot steps of a block touch only its own 8 rows (thread = (row r of the block,
+  // column c): one complex multiply-add per step, so a step is a short dependent chain instead of 32 FP64
+  // multiply-adds per thread); the rank-8 update of everything below is then done on DMMA by all warps:
+  //   A[i][k] -= sum_p conj(U[p][i]) / d_p * U[p][k]      (i <= k: upper 8 x 8 tiles only)
   const int k = tid & (CI_N - 1), i0 = (tid / CI_N) * (CI_N * CI_N / CI_THREADS);
-  constexpr int RPT = CI_N * CI_N / CI_THREADS;  // rows per thread (8)
+  constexpr int RPT = CI_N * CI_N / CI_THREADS;  // rows per thread of the final scaling (8)
+  __shared__ double s_ipiv[CI_N];
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   bool bad = false;
-  for (int j = 0; j < CI_N; ++j) {
-    __syncthreads();
-    const double piv = N_::real(A[j * CI_P + j]);
-    if (!(piv > rel_floor * diag0[j]) || !(piv > abs_floor)) bad = true;
-    // rows of this thread inside the active triangle: j < i <= k (whole warps drop out as j advances)
-    const int ilo = (i0 > j + 1) ? i0 : j + 1, ihi = (i0 + RPT - 1 < k) ? i0 + RPT - 1 : k;
-    if (ilo <= ihi) {
+  for (int kb = 0; kb < CI_N / 8; ++kb) {
+    const int j0 = kb * 8;
+    const int pr = tid >> 6, pc = tid & 63;   // panel row (0..7) and column of this thread
+    for (int t = 0; t < 8; ++t) {
+      const int j = j0 + t;
+      __syncthreads();
+      const double piv = N_::real(A[j * CI_P + j]);
+      if (!(piv > rel_floor * diag0[j]) || !(piv > abs_floor)) bad = true;
       const double ipiv = __drcp_rn(piv);
-      const T rjk = N_::scale(A[j * CI_P + k], ipiv);
-      for (int i = ilo; i <= ihi; ++i) A[i * CI_P + k] = N_::sub(A[i * CI_P + k], N_::mul(N_::conj(A[j * CI_P + i]), rjk));
+      if (tid == 0) s_ipiv[j] = ipiv;
+      const int i = j0 + pr;
+      if (pr > t && pc >= i)
+        A[i * CI_P + pc] = N_::sub(A[i * CI_P + pc], N_::mul(N_::conj(A[j * CI_P + i]), N_::scale(A[j * CI_P + pc], ipiv)));
+    }
+    __syncthreads();
+    const int nt = CI_N / 8 - 1 - kb;   // tiles per dimension of the trailing matrix
+    for (int tile = warp; tile < nt * (nt + 1) / 2; tile += CI_THREADS / 32) {
+      int mi = 0, rem = tile;           // tile (mi <= nj) of the upper triangle, row-major
+      while (rem >= nt - mi) { rem -= nt - mi; ++mi; }
+      const int nj = mi + rem;
+      const int I0 = j0 + 8 + mi * 8, K0 = j0 + 8 + nj * 8;
+      double acc[CPLX_CI<T>::value ? 4 : 2] = {};
+#pragma unroll
+      for (int p0 = 0; p0 < 8; p0 += 4) {
+        const int p = j0 + p0 + tq;
+        const T a = N_::scale(N_::conj(A[p * CI_P + I0 + gq]), s_ipiv[p]);
+        const T b = A[p * CI_P + K0 + gq];
+        if constexpr (CPLX_CI<T>::value) {
+          dmma884(acc[0], acc[1], a.x, b.x);
+          dmma884(acc[0], acc[1], -a.y, b.y);
+          dmma884(acc[2], acc[3], a.x, b.y);
+          dmma884(acc[2], acc[3], a.y, b.x);
+        } else {
+          dmma884(acc[0], acc[1], a, b);
+        }
+      }
+      T* c = A + (I0 + gq) * CI_P + K0 + 2 * tq;
+      if constexpr (CPLX_CI<T>::value) {
+        c[0] = N_::sub(c[0], make_double2(acc[0], acc[2]));
+        c[1] = N_::sub(c[1], make_double2(acc[1], acc[3]));
+      } else {
+        c[0] -= acc[0];
+        c[1] -= acc[1];
+      }
     }
   }
   __syncthreads();
@@ -1058,7 +1096,9 @@ __global__ void __launch_bounds__(CI_THREADS) chol_inv_kernel(const T* G, int64_
   }
   // X = A^-1 by recursive doubling over diagonal blocks of size b = 1, 2, .. 32:
   //   X12 = -X11 (A12 X22) for every pair of adjacent diagonal blocks
-  for (int b = 1; b < CI_N; b *= 2) {
+  // b < 8: one thread per entry; b >= 8: the two products run on DMMA, one 8 x 8 output tile per warp
+  // (32 / b block pairs x (b / 8)^2 tiles = b / 2 tiles; the zeros below the diagonals of X11 / X22 are stored)
+  for (int b = 1; b < 8; b *= 2) {
     const int nent = CI_N * b / 2;
     for (int e = tid; e < nent; e += CI_THREADS) {
       const int blk = e / (b * b), r = (e / b) % b, c = e % b;
@@ -1074,6 +1114,46 @@ __global__ void __launch_bounds__(CI_THREADS) chol_inv_kernel(const T* G, int64_
       T sum = N_::zero();
       for (int q = r; q < b; ++q) sum = N_::fma(X[(s0 + r) * CI_P + s0 + q], Y[(s0 + q) * CI_P + s0 + b + c], sum);
       X[(s0 + r) * CI_P + s0 + b + c] = N_::sub(N_::zero(), sum);
+    }
+    __syncthreads();
+  }
+  // C[rc.., cc..] = sgn * P[rp.., cp..] (b x b) * Q[rq.., cq..] (b x b), tile (mi, nj) of 8 x 8, all in shared memory
+  auto tile_product = [&](T* Cm, int rc, int cc, const T* Pm, int rp, int cp, const T* Qm, int rq, int cq, int b, int mi,
+                          int nj, double sgn) {
+    double acc[CPLX_CI<T>::value ? 4 : 2] = {};
+    for (int k0 = 0; k0 < b; k0 += 4) {
+      const T a = Pm[(rp + mi * 8 + gq) * CI_P + cp + k0 + tq];
+      const T q = Qm[(rq + k0 + tq) * CI_P + cq + nj * 8 + gq];
+      if constexpr (CPLX_CI<T>::value) {
+        dmma884(acc[0], acc[1], a.x, q.x);
+        dmma884(acc[0], acc[1], -a.y, q.y);
+        dmma884(acc[2], acc[3], a.x, q.y);
+        dmma884(acc[2], acc[3], a.y, q.x);
+      } else {
+        dmma884(acc[0], acc[1], a, q);
+      }
+    }
+    T* c = Cm + (rc + mi * 8 + gq) * CI_P + cc + nj * 8 + 2 * tq;
+    if constexpr (CPLX_CI<T>::value) {
+      c[0] = make_double2(sgn * acc[0], sgn * acc[2]);
+      c[1] = make_double2(sgn * acc[1], sgn * acc[3]);
+    } else {
+      c[0] = sgn * acc[0];
+      c[1] = sgn * acc[1];
+    }
+  };
+  for (int b = 8; b < CI_N; b *= 2) {
+    const int tpb = (b / 8) * (b / 8), ntile = (CI_N / (2 * b)) * tpb;
+    for (int tile = warp; tile < ntile; tile += CI_THREADS / 32) {
+      const int blk = tile / tpb, tt = tile - blk * tpb, mi = tt / (b / 8), nj = tt - mi * (b / 8);
+      const int s0 = blk * 2 * b;
+      tile_product(Y, s0, s0 + b, A, s0, s0 + b, X, s0 + b, s0 + b, b, mi, nj, 1.0);    // Y12 = A12 X22
+    }
+    __syncthreads();
+    for (int tile = warp; tile < ntile; tile += CI_THREADS / 32) {
+      const int blk = tile / tpb, tt = tile - blk * tpb, mi = tt / (b / 8), nj = tt - mi * (b / 8);
+      const int s0 = blk * 2 * b;
+      tile_product(X, s0, s0 + b, X, s0, s0, Y, s0, s0 + b, b, mi, nj, -1.0);           // X12 = -X11 Y12
     }
     __syncthreads();
   }
@@ -1193,11 +1273,9 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   TNB_CUDA_CHECK(cudaMemsetAsync(Rg, 0, (size_t)k * n * sizeof(T), st));
   auto kern = chol_inv_kernel<T>;
   constexpr size_t ci_smem = (size_t)3 * CI_N * CI_P * sizeof(T);
-  constexpr size_t ps_smem_bytes = (size_t)(PS_ROWS * PS_WP + PS_N * PsPitch<T>::RP) * sizeof(T);
   static PerDeviceOnce once;
   if (once.need()) {
     TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ci_smem));
-    TNB_CUDA_CHECK(cudaFuncSetAttribute(panel_scale_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem_bytes));
     once.done();
   }
   // the small factor of a pass: G (ld ldg) -> Rout (ld ldr), R^-1 -> Rinv (ld LDB)
@@ -1244,7 +1322,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       if (r_) return r_;
       // W <- (W - Qq C) R^-1, in place
       if (b <= PS_N) {
-        TNB_CUDA_CHECK(launch_k(panel_scale_kernel<T>, dim3((unsigned)((m + PS_ROWS - 1) / PS_ROWS)), dim3(128), ps_smem_bytes, st,
+        TNB_CUDA_CHECK(launch_k(panel_scale_kernel<T>, dim3((unsigned)((m + PS_ROWS - 1) / PS_ROWS)), dim3(256), 0, st,
                                 Qp, ldq, m, (int)b, (const T*)Ri, LDB));
         TNB_LAUNCH_CHECK();
         return 0;
