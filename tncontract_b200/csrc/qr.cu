@@ -1176,12 +1176,14 @@ __global__ void scale_by_kernel(T* x, int64_t n, const double* s) {
 struct QrSide {
   int dev = -1;
   cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
   int get(int device) {
     if (dev == device && s) return 0;
     TNB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     TNB_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
     TNB_CUDA_CHECK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    TNB_CUDA_CHECK(cudaEventCreateWithFlags(&fork2, cudaEventDisableTiming));
+    TNB_CUDA_CHECK(cudaEventCreateWithFlags(&join2, cudaEventDisableTiming));
     dev = device;
     return 0;
   }
@@ -1369,6 +1371,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     // [earlier groups, itself] is I + E with tiny E and the first-order factor R2 = I + U serves for any
     // width -- a quarter of the second-pass launches, and GEMMs with N = 256.  |E| > 1e-8 anywhere raises the
     // flag (the caller then repeats the factorisation with two passes per block).
+    bool rfix_pending = false;
     for (int64_t g0 = 0; g0 < k; g0 += QR_GB) {
       const int64_t bg = (k - g0 < QR_GB) ? (k - g0) : QR_GB;
       copy2d_kernel<T><<<blocks_for(m * bg), 256, 0, st>>>((const T*)A + g0, lda, Qb + g0, ldq, m, bg, sc);
@@ -1392,19 +1395,36 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
         rc = pass(q0, j0, bj, Qb + j0, Rg + q0 * n + j0, n, Factor{0, Rg + j0 * n + j0, n, 1e-10, 0.0, 0.0});
         if (rc) return rc;
       }
+      if (rfix_pending) {   // the previous group's R update still reads Sb / R2 / Rt, which this pass overwrites
+        TNB_CUDA_CHECK(cudaStreamWaitEvent(st, side.join2, 0));
+        rfix_pending = false;
+      }
       rc = pass(0, g0, bg, Qb + g0, Sb, LDB, Factor{1, R2, LDB, 0.0, 0.0, 1e-8});
       if (rc) return rc;
-      // R[G, G] = R2 R1g,  R[:g0, G] = C1 + C2 R1g   (R1g = the group's first-pass factor, now in R[G, G])
+      // R[G, G] = R2 R1g,  R[:g0, G] = C1 + C2 R1g   (R1g = the group's first-pass factor, now in R[G, G]).
+      // Nothing of the factorisation reads these entries of R again, so the three short kernels run on the side
+      // stream, next to the first blocks of the following group (they cost ~60 us per group on the main stream).
+      cudaStream_t sr = st;
+      if (overlap) {
+        TNB_CUDA_CHECK(cudaEventRecord(side.fork2, st));
+        TNB_CUDA_CHECK(cudaStreamWaitEvent(side.s, side.fork2, 0));
+        sr = side.s;
+      }
       T* Rgg = Rg + g0 * n + g0;
-      copy2d_kernel<T><<<blocks_for(bg * bg), 256, 0, st>>>(Rgg, n, Rt, LDB, bg, bg, nullptr);
+      copy2d_kernel<T><<<blocks_for(bg * bg), 256, 0, sr>>>(Rgg, n, Rt, LDB, bg, bg, nullptr);
       TNB_LAUNCH_CHECK();
-      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, bg, bg, bg, 1, 0, R2, LDB, 0, Rt, LDB, 0, 0, 0, Rgg, n, 0, 1, st);
+      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, bg, bg, bg, 1, 0, R2, LDB, 0, Rt, LDB, 0, 0, 0, Rgg, n, 0, 1, sr);
       if (rc) return rc;
       if (g0 > 0) {
-        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, g0, bg, bg, 1, 0, Sb, LDB, 0, Rt, LDB, 0, 1, 0, Rg + g0, n, 0, 1, st);
+        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, g0, bg, bg, 1, 0, Sb, LDB, 0, Rt, LDB, 0, 1, 0, Rg + g0, n, 0, 1, sr);
         if (rc) return rc;
       }
+      if (overlap) {
+        TNB_CUDA_CHECK(cudaEventRecord(side.join2, side.s));
+        rfix_pending = true;
+      }
     }
+    if (rfix_pending) TNB_CUDA_CHECK(cudaStreamWaitEvent(st, side.join2, 0));
   }
   if (n > k) {  // wide: R[:, k:] = Q^H (scale * A[:, k:])
     copy2d_kernel<T><<<blocks_for(m * (n - k)), 256, 0, st>>>((const T*)A + k, lda, Wsc, L.ldw, m, n - k, sc);
