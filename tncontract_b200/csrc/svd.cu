@@ -71,6 +71,7 @@ constexpr int JT = 512;      // threads per CTA: 2 x (JP/2)^2 -- G blocks on the
 constexpr int JGP = JP + 4;  // pitch of W / Gram partials in shared memory (= 4 mod 8: conflict-free DMMA fragments)
 constexpr int JGG = JP + 1;  // pitch of G (rotation phase only): row AND column accesses are conflict-free
 constexpr int JWP = JP + 2;  // pitch of W (= 2 mod 8): the apply reads it transposed (fragment [k = p][m = q]) without conflicts
+constexpr int JSP = JP + 4;  // pitch of the re + im table of W (doubles; = 4 mod 32: the four k rows of a fragment hit different banks)
 constexpr int JPAD = 4;      // panel pitch = CH + JPAD for the same reason
 constexpr int MAX_SWEEPS = 60;
 
@@ -677,8 +678,23 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   } else {
     rotation_phase<T, T>(G, JP * JGP, W, s_rc, s_rsp, cx, cluster, state, warp, lane);
   }
+  T* const Wfree = W + ((nsteps & 1) ^ 1) * (JP * JGP);   // the buffer the last step read: free from here on
   W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
+#else
+  T* const Wfree = W + JP * JGP;
 #endif
+  // re + im of every entry of W, formed ONCE: the third product of the 3-multiplication form needs it as an A
+  // fragment in every k-step of every 8-column block of the apply (non-tensor FP64 adds share the pipe with the
+  // DMMAs: they were the largest single source of pipe-throttle stalls of the round)
+  double* const Wsum = reinterpret_cast<double*>(Wfree);   // [JP][JSP]
+  if constexpr (CPLX) {
+    for (int idx = tid; idx < JP * JP; idx += JT) {
+      const int p_ = idx / JP, q_ = idx - p_ * JP;
+      const T w = W[p_ * JWP + q_];
+      Wsum[p_ * JSP + q_] = w.x + w.y;
+    }
+    __syncthreads();
+  }
   JSTAMP(75, threadIdx.x == 0);
   if (crank == 0) {
     state = __reduce_or_sync(0xffffffffu, state);
@@ -722,7 +738,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
             for (int mt = 0; mt < 4; ++mt) {
               dmma884(acc[mt][0], acc[mt][1], av[mt].x, bv.x);
               dmma884(acc[mt][2], acc[mt][3], av[mt].y, bv.y);
-              dmma884(acc[mt][4], acc[mt][5], av[mt].x + av[mt].y, bs);
+              dmma884(acc[mt][4], acc[mt][5], Wsum[(k0 + tq) * JSP + mt * 8 + gq], bs);
             }
           } else {
 #pragma unroll
