@@ -622,6 +622,15 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     auto plan = [&](int64_t tiles, bool small_tile) {
       const int64_t capacity = (int64_t)sm_count() * (small_tile ? 2 : 1);
       int64_t want = capacity / tiles;
+      if (want < 1 && !small_tile && tiles < 2 * capacity) {
+        // between one and two waves of full-size tiles (192 tiles on 148 SMs run at 65 %): a 2-4 way split that
+        // lands just under a whole number of waves buys that back; the partials stay small next to the product
+        double best = (double)tiles / (double)(((tiles + capacity - 1) / capacity) * capacity) + 0.15;
+        for (int64_t s_ = 2; s_ <= 4; ++s_) {
+          const double eff = (double)(tiles * s_) / (double)(((tiles * s_ + capacity - 1) / capacity) * capacity);
+          if (eff > best) { best = eff; want = s_; }
+        }
+      }
       if (want > max_by_k) want = max_by_k;
       if (want > max_by_ws) want = max_by_ws;
       if (want > 64) want = 64;

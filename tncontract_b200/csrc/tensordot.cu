@@ -17,6 +17,9 @@ namespace tnb {
 
 int permute_view(int dtype, const void* in, int rank, const int64_t* oshape, const int64_t* istride, void* out,
                  double ar, double ai, int conj, cudaStream_t st);
+int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
+            int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
+            int64_t sC, int64_t batch, void* splitk_ws, size_t splitk_bytes, cudaStream_t st);
 int gemm(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double ar, double ai, const void* A,
          int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double br, double bi, void* C, int64_t ldc,
          int64_t sC, int64_t batch, cudaStream_t st);
@@ -95,6 +98,7 @@ struct DotPlan {
   OperandPlan pa, pb;
   bool copy_a, copy_b;
   size_t ws_a, ws_b;
+  size_t ws_sk;   // split-K scratch (complex products between one and two waves of full-size tiles, see gemm_ws)
 };
 
 static int make_plan(const tnb_tensor_t* a, const tnb_tensor_t* b, int nctr, const int32_t* axes_a,
@@ -161,6 +165,13 @@ static int make_plan(const tnb_tensor_t* a, const tnb_tensor_t* b, int nctr, con
   const size_t es = elem_size(a->dtype);
   P->ws_a = P->copy_a ? (((size_t)numel(a) * es + 255) & ~(size_t)255) : 0;
   P->ws_b = P->copy_b ? (((size_t)numel(b) * es + 255) & ~(size_t)255) : 0;
+  // un-batched complex products whose full-size tiles fill between one and two waves get room for four partials
+  P->ws_sk = 0;
+  const bool batched = (P->pa.ok && P->pa.nbatch > 1) || (P->pb.ok && P->pb.nbatch > 1);
+  if (a->dtype == TNB_C128 && !batched && P->K >= 512) {
+    const int64_t tiles = ((P->M + 127) / 128) * ((P->N + 63) / 64), cap = sm_count();
+    if (tiles > cap && tiles < 2 * cap) P->ws_sk = (4 * (size_t)P->M * P->N * es + 255) & ~(size_t)255;
+  }
   return 0;
 }
 
@@ -172,7 +183,7 @@ extern "C" size_t tnb_tensordot_workspace(const tnb_tensor_t* a, const tnb_tenso
                                           const int32_t* axes_a, const int32_t* axes_b) {
   DotPlan P;
   if (make_plan(a, b, nctr, axes_a, axes_b, &P) != 0) return 0;
-  return P.ws_a + P.ws_b;
+  return P.ws_a + P.ws_b + P.ws_sk;
 }
 
 extern "C" int tnb_tensordot(const tnb_tensor_t* a, const tnb_tensor_t* b, int nctr, const int32_t* axes_a,
@@ -184,6 +195,8 @@ extern "C" int tnb_tensordot(const tnb_tensor_t* a, const tnb_tensor_t* b, int n
   if (P.M == 0 || P.N == 0) return 0;
   if (!out) return TNB_E_ARG;
   if (P.ws_a + P.ws_b > ws_bytes || (P.ws_a + P.ws_b > 0 && !ws)) return TNB_E_WORKSPACE;
+  const size_t sk_bytes = (ws && ws_bytes >= P.ws_a + P.ws_b + P.ws_sk) ? P.ws_sk : 0;   // optional: a caller may pass less
+  void* const sk = sk_bytes ? (char*)ws + P.ws_a + P.ws_b : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   const int dtype = a->dtype;
   const bool cplx = dtype == TNB_C128;
@@ -223,6 +236,6 @@ extern "C" int tnb_tensordot(const tnb_tensor_t* a, const tnb_tensor_t* b, int n
   } else if (pb.nbatch > 1) {   // C[m, (bb, n')]
     batch = pb.nbatch; sB = pb.bstride; Ng = pb.mn; sC = pb.mn;
   }
-  return gemm(dtype, opA, opB, Mg, Ng, P.K, 1.0, 0.0, Aptr, pa.ld, sA, Bptr, pb.ld, sB, 0.0, 0.0, out, ldc, sC, batch,
-              st);
+  return gemm_ws(dtype, opA, opB, Mg, Ng, P.K, 1.0, 0.0, Aptr, pa.ld, sA, Bptr, pb.ld, sB, 0.0, 0.0, out, ldc, sC, batch,
+                 batch == 1 ? sk : nullptr, batch == 1 ? sk_bytes : 0, st);
 }
