@@ -372,7 +372,7 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
 }
 
 
-// Shared memory: P[JP][CH+JPAD] | G[2][JP][JGP] | W[2][JP][JGP]  (the cluster-reduction partials live in W's space)
+// Shared memory: P[JP][CH+JPAD] | G[2][JP][JGP] | W[2][JP][JGP] | Gpart[GRAM_TILES][64] (this CTA's Gram partial)
 template <typename T>
 __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   typedef Num<T> N_;
@@ -391,7 +391,8 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   T* P = reinterpret_cast<T*>(smem_raw);
   T* G = P + (size_t)JP * pitch;   // G and W are double-buffered through the sweep: [2][JP][JGP] each
   T* W = G + 2 * JP * JGP;
-  T* Gpart = W;
+  T* Gpart = W + 2 * JP * JGP;   // [GRAM_TILES][64]: own buffer, so that W is initialised before the cluster meets and
+                                 // nobody has to wait for the remote readers of its partial
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   // s_rr[step][a] = (smaller, larger) panel column of rotation pair a in step `step`.
@@ -587,7 +588,11 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     T sum = N_::zero();
     for (int w = (8 * t) / GRAM_UPW; w <= (8 * t + 7) / GRAM_UPW; ++w)
       sum = N_::add(sum, slots[(w * 2 + ((((w * GRAM_UPW) >> 3) == t) ? 0 : 1)) * 64 + e]);
-    Gpart[(gm * 8 + (e >> 3)) * JGP + gn * 8 + (e & 7)] = sum;
+    Gpart[idx] = sum;
+  }
+  for (int idx = tid; idx < JP * JP; idx += JT) {
+    const int i = idx / JP, j = idx - i * JP;
+    W[i * JWP + j] = (i == j) ? N_::one() : N_::zero();
   }
   cluster.sync();
   // sum of the cluster's partials (same order in every CTA: identical bits everywhere), mirrored into
@@ -600,7 +605,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     if (i > j) continue;
     T part[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) part[q] = (q < S) ? cluster.map_shared_rank(Gpart, q)[i * JGP + j] : N_::zero();
+    for (int q = 0; q < 8; ++q) part[q] = (q < S) ? cluster.map_shared_rank(Gpart, q)[idx] : N_::zero();
     T sum = part[0];
 #pragma unroll
     for (int q = 1; q < 8; ++q) sum = N_::add(sum, part[q]);
@@ -611,12 +616,9 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
       G[j * JGG + i] = N_::conj(sum);
     }
   }
-  cluster.sync();  // all remote reads done before any CTA overwrites its partials (or exits)
+  // No second cluster barrier: nobody overwrites its partial in this launch, and no CTA leaves before the barrier that
+  // ends the rotation phase (S > 1 always exchanges the rows of W there), by which time every reader is done.
   JSTAMP(74, threadIdx.x == 0);
-  for (int idx = tid; idx < JP * JP; idx += JT) {
-    const int i = idx / JP, j = idx - i * JP;
-    W[i * JWP + j] = (i == j) ? N_::one() : N_::zero();
-  }
   __syncthreads();
 
   // ---- parallel-ordered Jacobi rotations on G, accumulated in W (rotation_phase above) -------------------
@@ -678,6 +680,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   } else {
     rotation_phase<T, T>(G, JP * JGP, W, s_rc, s_rsp, cx, cluster, state, warp, lane);
   }
+  if (S > 1 && !cx.wsplit) cluster.sync();   // cluster sizes that do not split W: still nobody may leave while its partial is read
   T* const Wfree = W + ((nsteps & 1) ^ 1) * (JP * JGP);   // the buffer the last step read: free from here on
   W += (nsteps & 1) * (JP * JGP);  // the buffer the last step wrote
 #else
@@ -947,7 +950,7 @@ template <typename T>
 static int configure_round_kernel(JacobiDeviceInfo& di) {
   constexpr int dt = sizeof(T) == 16 ? 1 : 0;
   if (di.configured[dt]) return 0;
-  TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024));
   TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
   di.configured[dt] = true;
   return 0;
@@ -1039,7 +1042,7 @@ static JacobiPlan jacobi_plan(int64_t n, int64_t L, bool with_v, int batch) {
   const int ch_max = cplx ? 256 : 512;
   const int64_t longest = (L > n || !with_v) ? L : n;
   auto chunks = [&](int ch) { return (int)((L + ch - 1) / ch) + (with_v ? (int)((n + ch - 1) / ch) : 0); };
-  auto smem_for = [&](int ch) { return ((size_t)JP * (ch + JPAD) + 4 * (size_t)JP * JGP) * sizeof(T); };
+  auto smem_for = [&](int ch) { return ((size_t)JP * (ch + JPAD) + 4 * (size_t)JP * JGP + GRAM_TILES * 64) * sizeof(T); };
   // CTAs per cluster (<= 8): every pair's cluster (of every matrix of the batch) should be resident at once
   // (a second wave would double the round), so candidate sizes are checked against
   // cudaOccupancyMaxActiveClusters -- GPCs differ in SM count, so this is not simply SMs / size.  The chunk is
