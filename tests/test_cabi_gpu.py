@@ -115,6 +115,45 @@ def test_gemm_all_ops(cplx):
     assert rel(C.cpu().numpy(), ref) < TOL
 
 
+def test_gemm_full_size_tiles_tma():
+    """complex128 products with >= 148 full-size (128 x 64) tiles take the TMA-fed kernel: ragged M / N / K edges
+    (zero fill of out-of-bounds boxes), all 16 operand layouts / conjugations, padded leading dimensions, a
+    strided batch, and a broadcast operand (batch stride 0: no tensor map, cp.async kernel, same result)."""
+    torch, _lib, dv = _mods()
+    lib = _lib.load()
+    rng = np.random.default_rng(14)
+    op = lambda x, o: x if o == 0 else x.T if o == 1 else x.conj().T if o == 2 else x.conj()
+    al = (ctypes.c_double * 2)(0.5, -1.5)
+    be = (ctypes.c_double * 2)(0.25, 0.75)
+    alpha, beta = 0.5 - 1.5j, 0.25 + 0.75j
+    for (M, N, K) in [(1500, 1100, 70), (1290, 1030, 257)]:
+        C0 = rnd(rng, (M, N), True)
+        for oa in range(4):
+            for ob in range(4):
+                sa = (M, K) if oa in (0, 3) else (K, M)
+                sb = (K, N) if ob in (0, 3) else (N, K)
+                Af = rnd(rng, (sa[0], sa[1] + 3), True)     # padded leading dimensions
+                Bf = rnd(rng, (sb[0], sb[1] + 5), True)
+                A, B = torch.from_numpy(Af).cuda(), torch.from_numpy(Bf).cuda()
+                C = torch.from_numpy(C0.copy()).cuda()
+                rc = lib.tnb_gemm(1, oa, ob, M, N, K, al, A.data_ptr(), sa[1] + 3, 0, B.data_ptr(), sb[1] + 5, 0, be,
+                                  C.data_ptr(), N, 0, 1, dv.stream_ptr())
+                assert rc == 0
+                ref = alpha * op(Af[:, :sa[1]], oa) @ op(Bf[:, :sb[1]], ob) + beta * C0
+                assert rel(C.cpu().numpy(), ref) < TOL, (M, N, K, oa, ob)
+    # strided batch (3 x 60 tiles) and a broadcast B
+    M, N, K, nb = 640, 760, 130, 3
+    As, Bs = rnd(rng, (nb, M, K), True), rnd(rng, (nb, K, N), True)
+    A, B = torch.from_numpy(As).cuda(), torch.from_numpy(Bs).cuda()
+    one, zero = (ctypes.c_double * 2)(1, 0), (ctypes.c_double * 2)(0, 0)
+    for sB, ref in ((K * N, np.einsum("bmk,bkn->bmn", As, Bs)), (0, np.einsum("bmk,kn->bmn", As, Bs[0]))):
+        C = torch.full((nb, M, N), float("nan"), dtype=torch.complex128, device="cuda")
+        rc = lib.tnb_gemm(1, 0, 0, M, N, K, one, A.data_ptr(), K, M * K, B.data_ptr(), N, sB, zero, C.data_ptr(), N, M * N, nb,
+                          dv.stream_ptr())
+        assert rc == 0
+        assert rel(C.cpu().numpy(), ref) < TOL
+
+
 @pytest.mark.parametrize("cplx", [False, True])
 def test_gemm_split_k(cplx):
     """tnb_gemm_ws: Gram-like shapes (few C tiles, long K) cut along K over grid.z and reduced by the second kernel --
