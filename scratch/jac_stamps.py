@@ -21,3 +21,6 @@ ph = ["entry", "prologue done", "griddep wait done", "load+Gram done", "reductio
 for i in range(1, 7):
     print("%-20s +%6d cycles (%.2f us)" % (ph[i], t[70 + i] - t[70 + i - 1], (t[70 + i] - t[70 + i - 1]) / 1965.0))
 print("kernel body total %.2f us" % ((t[76] - t[70]) / 1965.0))
+if t[80]:
+    print("G task of warp 0, step 5: begin +%d after the step's start stamp | operands loaded +%d | block computed +%d | done +%d" %
+          (t[80] - t[21], t[81] - t[80], t[82] - t[80], t[23] - t[80]))

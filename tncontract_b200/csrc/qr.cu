@@ -1376,20 +1376,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       const int64_t bg = (k - g0 < QR_GB) ? (k - g0) : QR_GB;
       copy2d_kernel<T><<<blocks_for(m * bg), 256, 0, st>>>((const T*)A + g0, lda, Qb + g0, ldq, m, bg, sc);
       TNB_LAUNCH_CHECK();
-#ifdef TNB_EXP_QR_GROUPPROJ
-      // kernel experiment: the group is first projected against all earlier groups as a whole (two GEMMs with
-      // N = 256 instead of 2 x 4 with N = 64), the couplings landing in R[:g0, G]; the 64-column blocks then only
-      // meet the earlier blocks of their own group
-      const int64_t q0 = g0;
-      if (g0 > 0) {
-        rc = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, g0, bg, m, 1, 0, Qb, ldq, 0, Qb + g0, ldq, 0, 0, 0, Rg + g0, n, 0, 1, sk, sk_main, st);
-        if (rc) return rc;
-        rc = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, bg, g0, -1, 0, Qb, ldq, 0, Rg + g0, n, 0, 1, 0, Qb + g0, ldq, 0, 1, sk, sk_main, st);
-        if (rc) return rc;
-      }
-#else
-      const int64_t q0 = 0;
-#endif
+      const int64_t q0 = 0;   // (a group-level projection first, q0 = g0, was measured slower: the Cholesky then sits on the chain)
       for (int64_t j0 = g0; j0 < g0 + bg; j0 += QR_CB) {
         const int64_t bj = (g0 + bg - j0 < QR_CB) ? (g0 + bg - j0) : QR_CB;
         rc = pass(q0, j0, bj, Qb + j0, Rg + q0 * n + j0, n, Factor{0, Rg + j0 * n + j0, n, 1e-10, 0.0, 0.0});

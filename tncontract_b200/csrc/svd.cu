@@ -315,6 +315,7 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
       JSTAMP(2 + 4 * step, lane == 0);
     } else if (cx.g0 >= 0) {
       const int t = cx.g0 + lane;
+      JSTAMP(80, threadIdx.x == 0 && step == 5);
       if (t < NGB) {
         const int ta = g_ta, tb = g_tb;
         const int pa = cx.rr[step][ta][0], qa = cx.rr[step][ta][1];
@@ -324,6 +325,9 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
         Rb.c = s_rc[cur][tb]; Rb.sp = s_rsp[cur][tb];
         const GT msb = NG::sub(NG::zero(), NG::conj(Rb.sp));  // -conj(sp_b)
         const GT b00 = Gc[pa * JGG + pb], b01 = Gc[pa * JGG + qb], b10 = Gc[qa * JGG + pb], b11 = Gc[qa * JGG + qb];
+#ifdef TNB_EXP_STAMPS
+        if (blockIdx.x == 0 && threadIdx.x == 0 && step == 5) { g_jac_dbg[81] = clock64() + (long long)(NG::real(b00) * 0 + NG::real(b01) * 0 + NG::real(b10) * 0 + NG::real(b11) * 0 + Ra.c * 0 + Rb.c * 0); }
+#endif
         // T1 = B J_b:  T1[:,0] = c B[:,0] - conj(sp) B[:,1],  T1[:,1] = sp B[:,0] + c B[:,1]
         const GT t00 = rot_mix(Rb.c, b00, msb, b01), t01 = rot_mix(Rb.c, b01, Rb.sp, b00);
         const GT t10 = rot_mix(Rb.c, b10, msb, b11), t11 = rot_mix(Rb.c, b11, Rb.sp, b10);
@@ -331,6 +335,9 @@ __device__ __forceinline__ void rotation_phase(GT* G, int gbuf, T* W, typename N
         const GT msa = NG::sub(NG::zero(), Ra.sp), csa = NG::conj(Ra.sp);
         GT n00 = rot_mix(Ra.c, t00, msa, t10), n01 = rot_mix(Ra.c, t01, msa, t11);
         GT n10 = rot_mix(Ra.c, t10, csa, t00), n11 = rot_mix(Ra.c, t11, csa, t01);
+#ifdef TNB_EXP_STAMPS
+        if (blockIdx.x == 0 && threadIdx.x == 0 && step == 5) { g_jac_dbg[82] = clock64() + (long long)(NG::real(n00) * 0 + NG::real(n01) * 0 + NG::real(n10) * 0 + NG::real(n11) * 0); }
+#endif
         if (ta == tb) {
           // diagonal block: real diagonal, exact zero where a rotation was applied
           n00 = NG::from(NG::real(n00), 0);
@@ -642,6 +649,10 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   {
     const int g_warp[5] = {0, 4, 1, 5, 2};
     const int w_warp[10] = {8, 9, 10, 6, 12, 13, 14, 3, 7, 11};   // sub-partitions 0 1 2 2 0 1 2 3 3 3: the rotation warp (15, sub-partition 3) keeps its issue port to itself as long as possible
+    // (a step is ISSUE-bound: ~1250 issue slots of the five G warps, ~1200 of the four W warps, ~300 of the rotation
+    // warp over four sub-partitions ~ 690 cycles against 770 measured; other placements of the roles -- G on 0 0 1 1 0
+    // with W on 2, W next to the rotation warp, G on 0 1 2 3 0 -- came out at 29.40 / 28.78 / 28.94 us per round
+    // against 28.73)
 #pragma unroll
     for (int i = 0; i < 5; ++i) if (warp == g_warp[i]) cx.g0 = 32 * i;
 #pragma unroll
