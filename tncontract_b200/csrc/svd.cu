@@ -110,7 +110,7 @@ struct JacobiArgs {
   int64_t xstride, vstride;  // elements between consecutive matrices of a batch (blockIdx.y)
   int nblk;     // even number of column blocks (the last ones may be empty)
   int round;
-  int diag;     // 1: rotate the pairs INSIDE each of the two blocks (15 steps); 0: the 16 x 16 cross pairs (16 steps)
+  int diag;     // 1: rotate the pairs INSIDE each of the two blocks (15 steps); 0: the 16 x 16 cross pairs (16 steps); 2: both (31)
   int S;        // CTAs per cluster
   int CH;       // chunk length (power of two)
   int nx, nv;   // chunks per Xt row / per Vt row
@@ -406,12 +406,12 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   //   cross round: column a of block I meets column (a + step) mod 16 of block J      (16 steps)
   //   diag  round: two independent 16-player tournaments, one inside each block       (15 steps)
   // One diag round plus nblk - 1 cross rounds rotate every column pair exactly once per sweep.
-  __shared__ unsigned char s_rr[JB][JP / 2][2];
+  __shared__ unsigned char s_rr[2 * JB - 1][JP / 2][2];
   // s_pos[step][i] = 2 * (rotation pair holding panel column i in that step) + (1 if i is the larger one)
-  __shared__ unsigned char s_pos[JB][JP];
+  __shared__ unsigned char s_pos[2 * JB - 1][JP];
   // s_nxt[step][a]: for rotation pair a of step + 1, the two pairs of `step` its columns come from, their
   // columns, and on which side of its pair each column sits (packed, see below)
-  __shared__ unsigned int s_nxt[JB][JP / 2];
+  __shared__ unsigned int s_nxt[2 * JB - 1][JP / 2];
   // s_gt[t] = (ta, tb), ta <= tb: the 136 blocks of the upper block triangle of G (16 x 16 blocks of 2 x 2)
   __shared__ unsigned char s_gt[JB * (JB + 1) / 2][2];
   if (tid < JB * JB) {
@@ -422,16 +422,19 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
       s_gt[t][1] = (unsigned char)y;
     }
   }
-  const int nsteps = a.diag ? JB - 1 : JB;
+  // a.diag = 2: the in-block steps and then the cross steps in ONE round (31 steps on the same Gram matrix: the
+  // first launch of a sweep -- its pairs are those of cross round 0 -- so a sweep is nblk - 1 launches, not nblk)
+  const int nd = (a.diag != 0) ? JB - 1 : 0;
+  const int nsteps = nd + ((a.diag != 1) ? JB : 0);
   if (tid < nsteps * (JP / 2)) {
     const int st_ = tid / (JP / 2), pr_ = tid % (JP / 2);
     int x, y;
-    if (a.diag) {
+    if (st_ < nd) {
       rr_pair(JB, st_, pr_ & (JB / 2 - 1), x, y);
       if (pr_ >= JB / 2) { x += JB; y += JB; }
     } else {
       x = pr_;
-      y = JB + ((pr_ + st_) & (JB - 1));
+      y = JB + ((pr_ + st_ - nd) & (JB - 1));
     }
     const int lo_ = x < y ? x : y, hi_ = x < y ? y : x;
     s_rr[st_][pr_][0] = (unsigned char)lo_;
@@ -961,7 +964,11 @@ template <typename T>
 static int configure_round_kernel(JacobiDeviceInfo& di) {
   constexpr int dt = sizeof(T) == 16 ? 1 : 0;
   if (di.configured[dt]) return 0;
-  TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024));
+  // everything an SM offers one CTA (227 KB) minus the kernel's static shared memory
+  cudaFuncAttributes fa;
+  TNB_CUDA_CHECK(cudaFuncGetAttributes(&fa, jacobi_round_kernel<T>));
+  TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)fa.sharedSizeBytes));
   TNB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
   di.configured[dt] = true;
   return 0;
@@ -1131,7 +1138,7 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, int64_t xstride, T* Vt, int64_t
   // conventional flop count of one sweep (full JP x JP Gram over L, W applied over L [+ n with V]; 8 real
   // flops per complex multiply-add): what the profile credits per EXECUTED sweep
   const double sweep_flops = (cplx ? 8.0 : 2.0) * (double)JP * JP * (2.0 * (double)L + (Vt ? (double)n : 0.0)) *
-                             (double)p.npairs * (double)(p.rounds + 1);
+                             (double)p.npairs * (double)p.rounds;
   int hint;
   {
     std::lock_guard<std::mutex> lock(di.mu);
@@ -1146,9 +1153,9 @@ static int jacobi(T* Xt, int64_t ldx, int64_t L, int64_t xstride, T* Vt, int64_t
     {
       ProfScope prof(KC_JACOBI, st, 0.0);
       for (int s = 0; s < nq; ++s) {
-        for (int r = -1; r < p.rounds; ++r) {
-          a.diag = (r < 0);           // first the pairs inside the blocks (paired up as in round 0) ...
-          a.round = (r < 0) ? 0 : r;  // ... then every block against every other block
+        for (int r = 0; r < p.rounds; ++r) {
+          a.diag = (r == 0) ? 2 : 0;  // round 0 also rotates the pairs inside its blocks, before their cross pairs ...
+          a.round = r;                // ... then every block against every other block
           int rc = launch_round<T>(a, p.npairs, batch, p.smem, st);
           if (rc) return rc;
         }
