@@ -18,7 +18,10 @@
 // Xt (k x k) and Vt (k x k, starts as I), so a column is contiguous.  Columns
 // are grouped in blocks of JB = 16.  One sweep is a round-robin tournament
 // over block pairs (nblk - 1 rounds, nblk/2 independent pairs per round); one
-// kernel launch per round.  A pair is handled by one thread-block CLUSTER:
+// kernel launch per round -- the first round of a sweep also rotates the column
+// pairs INSIDE its blocks (15 steps before its 16 cross steps, on the same Gram
+// matrix), so every column pair is rotated exactly once per sweep.  A pair is
+// handled by one thread-block CLUSTER:
 //   * the 32 rows of the pair (both Xt and Vt, viewed as one long row) are cut
 //     into chunks of CH elements; each CTA of the cluster owns chunks
 //     crank, crank+S, ... and keeps the last Xt chunk it read resident in
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
   // s_rr[step][a] = (smaller, larger) panel column of rotation pair a in step `step`.
   //   cross round: column a of block I meets column (a + step) mod 16 of block J      (16 steps)
   //   diag  round: two independent 16-player tournaments, one inside each block       (15 steps)
-  // One diag round plus nblk - 1 cross rounds rotate every column pair exactly once per sweep.
+  // The in-block steps (once per sweep) plus nblk - 1 rounds of cross steps rotate every column pair exactly once per sweep.
   __shared__ unsigned char s_rr[2 * JB - 1][JP / 2][2];
   // s_pos[step][i] = 2 * (rotation pair holding panel column i in that step) + (1 if i is the larger one)
   __shared__ unsigned char s_pos[2 * JB - 1][JP];
