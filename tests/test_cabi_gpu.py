@@ -115,40 +115,45 @@ def test_gemm_all_ops(cplx):
     assert rel(C.cpu().numpy(), ref) < TOL
 
 
-def test_gemm_full_size_tiles_tma():
-    """complex128 products with >= 148 full-size (128 x 64) tiles take the TMA-fed kernel: ragged M / N / K edges
-    (zero fill of out-of-bounds boxes), all 16 operand layouts / conjugations, padded leading dimensions, a
-    strided batch, and a broadcast operand (batch stride 0: no tensor map, cp.async kernel, same result)."""
+@pytest.mark.parametrize("cplx", [False, True])
+def test_gemm_full_size_tiles_tma(cplx):
+    """Products with >= 148 full-size tiles (128 x 64 complex128, 128 x 128 float64) take the TMA-fed kernels: ragged
+    M / N / K edges (zero fill of out-of-bounds boxes), all operand layouts / conjugations, padded leading dimensions
+    (even: tensor maps; odd for float64: no tensor map, cp.async kernel), a strided batch, and a broadcast operand
+    (batch stride 0: cp.async kernel, same result)."""
     torch, _lib, dv = _mods()
     lib = _lib.load()
     rng = np.random.default_rng(14)
+    code, tdt = (1, torch.complex128) if cplx else (0, torch.float64)
     op = lambda x, o: x if o == 0 else x.T if o == 1 else x.conj().T if o == 2 else x.conj()
-    al = (ctypes.c_double * 2)(0.5, -1.5)
-    be = (ctypes.c_double * 2)(0.25, 0.75)
-    alpha, beta = 0.5 - 1.5j, 0.25 + 0.75j
-    for (M, N, K) in [(1500, 1100, 70), (1290, 1030, 257)]:
-        C0 = rnd(rng, (M, N), True)
+    alpha, beta = (0.5 - 1.5j, 0.25 + 0.75j) if cplx else (0.5, -1.25)
+    al = (ctypes.c_double * 2)(np.real(alpha), np.imag(alpha))
+    be = (ctypes.c_double * 2)(np.real(beta), np.imag(beta))
+    shapes = [(1500, 1100, 70), (1290, 1030, 257)] if cplx else [(1500, 1900, 70), (1290, 2000, 257)]
+    for (M, N, K) in shapes:
+        C0 = rnd(rng, (M, N), cplx)
         for oa in range(4):
             for ob in range(4):
-                sa = (M, K) if oa in (0, 3) else (K, M)
-                sb = (K, N) if ob in (0, 3) else (N, K)
-                Af = rnd(rng, (sa[0], sa[1] + 3), True)     # padded leading dimensions
-                Bf = rnd(rng, (sb[0], sb[1] + 5), True)
-                A, B = torch.from_numpy(Af).cuda(), torch.from_numpy(Bf).cuda()
-                C = torch.from_numpy(C0.copy()).cuda()
-                rc = lib.tnb_gemm(1, oa, ob, M, N, K, al, A.data_ptr(), sa[1] + 3, 0, B.data_ptr(), sb[1] + 5, 0, be,
-                                  C.data_ptr(), N, 0, 1, dv.stream_ptr())
-                assert rc == 0
-                ref = alpha * op(Af[:, :sa[1]], oa) @ op(Bf[:, :sb[1]], ob) + beta * C0
-                assert rel(C.cpu().numpy(), ref) < TOL, (M, N, K, oa, ob)
-    # strided batch (3 x 60 tiles) and a broadcast B
-    M, N, K, nb = 640, 760, 130, 3
-    As, Bs = rnd(rng, (nb, M, K), True), rnd(rng, (nb, K, N), True)
+                for pad_a, pad_b in ((2, 6), (3, 5)):
+                    sa = (M, K) if oa in (0, 3) else (K, M)
+                    sb = (K, N) if ob in (0, 3) else (N, K)
+                    Af = rnd(rng, (sa[0], sa[1] + pad_a), cplx)     # padded leading dimensions
+                    Bf = rnd(rng, (sb[0], sb[1] + pad_b), cplx)
+                    A, B = torch.from_numpy(Af).cuda(), torch.from_numpy(Bf).cuda()
+                    C = torch.from_numpy(C0.copy()).cuda()
+                    rc = lib.tnb_gemm(code, oa, ob, M, N, K, al, A.data_ptr(), sa[1] + pad_a, 0, B.data_ptr(), sb[1] + pad_b, 0,
+                                      be, C.data_ptr(), N, 0, 1, dv.stream_ptr())
+                    assert rc == 0
+                    ref = alpha * op(Af[:, :sa[1]], oa) @ op(Bf[:, :sb[1]], ob) + beta * C0
+                    assert rel(C.cpu().numpy(), ref) < TOL, (M, N, K, oa, ob, pad_a)
+    # strided batch and a broadcast B
+    M, N, K, nb = (640, 760, 130, 3) if cplx else (900, 1000, 130, 3)
+    As, Bs = rnd(rng, (nb, M, K), cplx), rnd(rng, (nb, K, N), cplx)
     A, B = torch.from_numpy(As).cuda(), torch.from_numpy(Bs).cuda()
     one, zero = (ctypes.c_double * 2)(1, 0), (ctypes.c_double * 2)(0, 0)
     for sB, ref in ((K * N, np.einsum("bmk,bkn->bmn", As, Bs)), (0, np.einsum("bmk,kn->bmn", As, Bs[0]))):
-        C = torch.full((nb, M, N), float("nan"), dtype=torch.complex128, device="cuda")
-        rc = lib.tnb_gemm(1, 0, 0, M, N, K, one, A.data_ptr(), K, M * K, B.data_ptr(), N, sB, zero, C.data_ptr(), N, M * N, nb,
+        C = torch.full((nb, M, N), float("nan"), dtype=tdt, device="cuda")
+        rc = lib.tnb_gemm(code, 0, 0, M, N, K, one, A.data_ptr(), K, M * K, B.data_ptr(), N, sB, zero, C.data_ptr(), N, M * N, nb,
                           dv.stream_ptr())
         assert rc == 0
         assert rel(C.cpu().numpy(), ref) < TOL

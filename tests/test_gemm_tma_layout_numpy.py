@@ -57,3 +57,57 @@ def test_sigma8_is_a_permutation_and_matches_the_epilogue():
     # accumulator pair of a lane = fragment columns 2 tq, 2 tq + 1 -> tile columns tq and 4 + tq
     for tq in range(4):
         assert sigma8(2 * tq) == tq and sigma8(2 * tq + 1) == 4 + tq
+
+
+# ---- float64 tile (gemm_tma_real_kernel): 8-byte elements, half-warps of 16 lanes -------------------------------------
+
+def sigma8r(g):
+    return ((g & 3) << 1) | (g >> 2)
+
+
+def pi16(parity, g):
+    return (parity << 2) | ((g & 2) << 2) | ((g & 4) >> 1) | (g & 1)
+
+
+def landed_tile_real(kc, bmn=128, bk=16):
+    """phys[byte offset // 8] = (mn, k) of the double the TMA boxes put there"""
+    phys = {}
+    for mn in range(bmn):
+        for k in range(bk):
+            if kc:      # one box {16 k, bmn rows}
+                off = swizzle128(mn * 128 + k * 8)
+            else:       # boxes {16 mn, 16 k rows} of 2 KB (two 1 KB swizzle atoms)
+                off = (mn // 16) * 2048 + swizzle128(k * 128 + (mn % 16) * 8)
+            phys[off // 8] = (mn, k)
+    assert len(phys) == bmn * bk
+    return phys
+
+
+def frag_off_real(kc, wbase, t, gq, k):
+    if kc:
+        r = wbase + t * 8 + sigma8r(gq)
+        return r * 128 + (((k >> 1) ^ (r & 7)) << 4) + ((k & 1) << 3)
+    box, p = (wbase >> 4) + (t >> 1), pi16(t & 1, gq)
+    return box * 2048 + k * 128 + (((p >> 1) ^ (k & 7)) << 4) + ((p & 1) << 3)
+
+
+def frag_pos(kc, t, g):
+    return t * 8 + sigma8r(g) if kc else (t >> 1) * 16 + pi16(t & 1, g)
+
+
+def test_real_fragment_loads_read_the_right_element_without_bank_conflicts():
+    for kc in (True, False):
+        tile = landed_tile_real(kc)
+        for wbase in (0, 32, 64, 96):
+            for t in range(4):
+                for kk in (0, 4, 8, 12):
+                    for half in range(2):
+                        slots = set()
+                        for lane in range(16 * half, 16 * half + 16):
+                            gq, tq = lane >> 2, lane & 3
+                            off = frag_off_real(kc, wbase, t, gq, kk + tq)
+                            assert tile[off // 8] == (wbase + frag_pos(kc, t, gq), kk + tq)
+                            slots.add((off // 8) % 16)
+                        assert len(slots) == 16
+    for kc in (True, False):   # the positions of a warp tile's fragments are a permutation of its rows
+        assert sorted(frag_pos(kc, t, g) for t in range(8) for g in range(8)) == list(range(64))

@@ -21,13 +21,13 @@
 //   MN-contiguous: pitch BMN+4 (real) / BMN+2 (complex)
 // Conjugation of either operand is a sign flip on the imaginary fragment.
 //
-// The full-size complex128 tile (the one that carries the sweeps) is fed by TMA instead
-// (gemm_tma_kernel): cp.async.bulk.tensor copies through two tensor maps (SASS UTMALDG), issued by
+// The full-size tiles (the ones that carry the sweeps) are fed by TMA instead (gemm_tma_kernel for
+// complex128, gemm_tma_real_kernel for float64: 28.3 -> 33.1 TFLOP/s on 8192^3): cp.async.bulk.tensor copies through two tensor maps (SASS UTMALDG), issued by
 // one thread, completing on per-stage mbarriers; six stages of dense 128-byte-swizzled tiles (no
 // padding: 24 KB per stage instead of 36).  Bank conflicts are avoided by the hardware swizzle plus
 // a fixed permutation of the rows inside every group of 8 (see sigma8), edges by the zero fill of
-// out-of-bounds boxes.  Anything a tensor map cannot describe (zero or unaligned strides) takes
-// the cp.async kernel.
+// out-of-bounds boxes.  Anything a tensor map cannot describe (zero or unaligned strides, odd
+// leading dimensions of float64 operands) and the small tiles take the cp.async kernel.
 // Algorithmic work: 2*M*N*K flop (real), 8*M*N*K flop (complex).
 #include <cuda.h>
 
@@ -514,6 +514,186 @@ static int try_gemm_tma(GemmArgs& g, bool a_kc, bool b_kc, int64_t batch, cudaSt
   return launch_gemm_tma<false, false>(g, ma, mb, batch, st);
 }
 
+// ---- TMA-fed variant of the full-size float64 tile (128 x 128 x 16, 8 warps as 2 x 4, warp tile 64 x 32) -------------
+// Stages of 16 KB + 16 KB, dense, 128-byte swizzle as above; an element is 8 bytes, so a fragment load is served a
+// HALF-warp at a time (fragment rows gq = 0..3 or 4..7, k = kk + tq) and its 16 lanes must hit 16 different 8-byte slots:
+//   K-contiguous  ([mn][k]): one box {16 k, 128 rows}; 16-byte chunk = (k >> 1) ^ (row & 7).  Fragment row gq -> tile
+//     row sigma8r(gq) = 2 (gq & 3) + (gq >> 2): four rows whose low bits are 0 2 4 6 (or 1 3 5 7) spread the two chunks
+//     of a k quadruple over all eight;
+//   MN-contiguous ([k][mn]): a box {16 mn, 16 k} of 2 KB per group of 16 rows; chunk = ((mn & 15) >> 1) ^ (k & 7).
+//     The fragment rows of TWO adjacent 8-row tiles map into one group of 16: pi16(tile parity, gq) =
+//     4 parity + [0 1 8 9 2 3 10 11][gq] -- rows {0,1,8,9} give chunks {0..3} and {4..7} in both halves of the pair.
+// The epilogue writes C through the same permutations (of the rows by A's layout, of the columns by B's).
+constexpr int TMAR_STAGES = 5;
+constexpr int TMAR_OP_BYTES = 128 * 16 * 8, TMAR_STAGE_BYTES = 2 * TMAR_OP_BYTES;
+__host__ __device__ __forceinline__ int sigma8r(int g) { return ((g & 3) << 1) | (g >> 2); }
+__host__ __device__ __forceinline__ int pi16(int parity, int g) { return (parity << 2) | ((g & 2) << 2) | ((g & 4) >> 1) | (g & 1); }
+// row (or column) of fragment index g of 8-tile t inside a warp tile, by the operand's layout
+template <bool KC> __device__ __forceinline__ int frag_pos(int t, int g) {
+  if constexpr (KC) return t * 8 + sigma8r(g);
+  else return (t >> 1) * 16 + pi16(t & 1, g);
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256) gemm_tma_real_kernel(GemmArgs g, const __grid_constant__ CUtensorMap mapA,
+                                                            const __grid_constant__ CUtensorMap mapB) {
+  constexpr int BM = 128, BN = 128, BK = 16, WM = 64, WN = 32, WARPS_N = 4;
+  constexpr int MT = WM / 8, NT = WN / 8;
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full[TMAR_STAGES];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const int tile = blockIdx.x;
+  const int tm = tile % g.tiles_m, tn = tile / g.tiles_m;
+  const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+  const int bz = (int)blockIdx.y;
+  double* Cg = reinterpret_cast<double*>(g.C) + (int64_t)bz * g.sC;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_per_split;
+  const int64_t kend = (g.splits > 1 && kbeg + g.k_per_split < g.K) ? kbeg + g.k_per_split : g.K;
+  int64_t ldc = g.ldc;
+  if (g.splits > 1) {
+    Cg = reinterpret_cast<double*>(g.part) + (int64_t)blockIdx.z * g.M * g.N;
+    ldc = g.N;
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TMAR_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  griddep_wait();
+  griddep_launch_dependents();
+
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  const int KT = (int)((kend - kbeg + BK - 1) / BK);
+  auto issue = [&](int kt) {   // thread 0 only
+    const int s = kt % TMAR_STAGES;
+    unsigned char* a_s = smem_raw + s * TMAR_STAGE_BYTES;
+    unsigned char* b_s = a_s + TMAR_OP_BYTES;
+    const int k0 = (int)(kbeg + (int64_t)kt * BK);
+    mbar_arrive_expect_tx(&full[s], TMAR_STAGE_BYTES);
+    if constexpr (A_KC) {
+      tma_load_3d(a_s, &mapA, k0, (int)m0, bz, &full[s]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BM / 16; ++j) tma_load_3d(a_s + j * 2048, &mapA, (int)m0 + 16 * j, k0, bz, &full[s]);
+    }
+    if constexpr (B_KC) {
+      tma_load_3d(b_s, &mapB, k0, (int)n0, bz, &full[s]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) tma_load_3d(b_s + j * 2048, &mapB, (int)n0 + 16 * j, k0, bz, &full[s]);
+    }
+  };
+  if (tid == 0) {
+    for (int s = 0; s < TMAR_STAGES && s < KT; ++s) issue(s);
+  }
+  // byte offset of fragment element (tile t of the warp, fragment index gq, k) inside an operand buffer
+  auto frag_off = [&](bool kc, int wbase, int t, int k) -> int {
+    if (kc) {
+      const int r = wbase + t * 8 + sigma8r(gq);
+      return r * 128 + ((((k >> 1) ^ (r & 7))) << 4) + ((k & 1) << 3);
+    }
+    const int box = (wbase >> 4) + (t >> 1), p = pi16(t & 1, gq);
+    return box * 2048 + k * 128 + ((((p >> 1) ^ (k & 7))) << 4) + ((p & 1) << 3);
+  };
+  for (int kt = 0; kt < KT; ++kt) {
+    const int s = kt % TMAR_STAGES;
+    mbar_wait_bounded(&full[s], (uint32_t)((kt / TMAR_STAGES) & 1));
+    const unsigned char* a_s = smem_raw + s * TMAR_STAGE_BYTES;
+    const unsigned char* b_s = a_s + TMAR_OP_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      const int k = kk + tq;
+      double af[MT], bf[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) af[i] = *reinterpret_cast<const double*>(a_s + frag_off(A_KC, wm * WM, i, k));
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bf[j] = *reinterpret_cast<const double*>(b_s + frag_off(B_KC, wn * WN, j, k));
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+    if (tid == 0 && kt + TMAR_STAGES < KT) issue(kt + TMAR_STAGES);
+  }
+  const bool has_beta = g.beta_r != 0.0 && g.splits <= 1;
+  const double alpha = g.splits > 1 ? 1.0 : g.alpha_r;
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int64_t row = m0 + wm * WM + frag_pos<A_KC>(i, gq);
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t col = n0 + wn * WN + frag_pos<B_KC>(j, 2 * tq + e);
+        if (col >= g.N) continue;
+        double* dst = Cg + row * ldc + col;
+        double v = alpha * acc[i][j][e];
+        if (has_beta) v += g.beta_r * dst[0];
+        dst[0] = v;
+      }
+    }
+  }
+}
+
+static bool make_operand_map_real(CUtensorMap* map, const void* base, bool kc, int64_t MN, int64_t K, int64_t ld, int64_t stride,
+                                  int64_t batch) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const int64_t inner = kc ? K : MN, outer = kc ? MN : K;
+  if (((uintptr_t)base & 15) != 0 || (ld & 1) != 0 || ld < inner || inner <= 0 || outer <= 0) return false;
+  if (inner >= (1LL << 31) || outer >= (1LL << 31) || batch >= (1LL << 31)) return false;
+  if (batch > 1 && (stride <= 0 || (stride & 1) != 0)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)batch};
+  const cuuint64_t row_bytes = (cuuint64_t)ld * 8;
+  const cuuint64_t strides[2] = {row_bytes, batch > 1 ? (cuuint64_t)stride * 8 : row_bytes * (cuuint64_t)outer};
+  if (strides[0] >= (1ULL << 40) || strides[1] >= (1ULL << 40)) return false;
+  const cuuint32_t box[3] = {16, (cuuint32_t)(kc ? 128 : 16), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool A_KC, bool B_KC>
+static int launch_gemm_tma_real(GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int64_t batch, cudaStream_t st) {
+  constexpr size_t smem = (size_t)TMAR_STAGES * TMAR_STAGE_BYTES + 1024;
+  auto kern = gemm_tma_real_kernel<A_KC, B_KC>;
+  static PerDeviceOnce once;
+  if (once.need()) {
+    TNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once.done();
+  }
+  g.tiles_m = (int)((g.M + 127) / 128);
+  g.tiles_n = (int)((g.N + 127) / 128);
+  dim3 grid((unsigned)(g.tiles_m * g.tiles_n), (unsigned)batch, (unsigned)(g.splits > 1 ? g.splits : 1));
+  TNB_CUDA_CHECK(launch_k(kern, grid, dim3(256), smem, st, g, ma, mb));
+  TNB_LAUNCH_CHECK();
+  return 0;
+}
+
+// The TMA path for the full-size float64 tile; returns -1 when it does not apply.
+static int try_gemm_tma_real(GemmArgs& g, bool a_kc, bool b_kc, int64_t batch, cudaStream_t st) {
+  if (batch > 65535) return -1;
+  CUtensorMap ma, mb;
+  if (!make_operand_map_real(&ma, g.A, a_kc, g.M, g.K, g.lda, g.sA, batch)) return -1;
+  if (!make_operand_map_real(&mb, g.B, b_kc, g.N, g.K, g.ldb, g.sB, batch)) return -1;
+  if (a_kc && b_kc) return launch_gemm_tma_real<true, true>(g, ma, mb, batch, st);
+  if (a_kc && !b_kc) return launch_gemm_tma_real<true, false>(g, ma, mb, batch, st);
+  if (!a_kc && b_kc) return launch_gemm_tma_real<false, true>(g, ma, mb, batch, st);
+  return launch_gemm_tma_real<false, false>(g, ma, mb, batch, st);
+}
+
 // C = alpha * sum_z part[z] + beta * C  (deterministic: fixed summation order)
 template <typename T>
 __global__ void splitk_reduce_kernel(const T* part, int splits, int64_t M, int64_t N, T* C, int64_t ldc, double ar,
@@ -669,6 +849,12 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     return finish(small ? dispatch_layout<true, true, true>(g, a_kc, b_kc, batch, st)
                         : dispatch_layout<true, false, true>(g, a_kc, b_kc, batch, st));
   }
+#ifndef TNB_EXP_NO_TMA
+  if (!small) {
+    const int rt = try_gemm_tma_real(g, a_kc, b_kc, batch, st);
+    if (rt >= 0) return finish(rt);
+  }
+#endif
   const bool vec = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                    (sA % 2 == 0 || batch == 1) && (sB % 2 == 0 || batch == 1);
   if (vec)
