@@ -327,7 +327,20 @@ def main():
 
     # ---- one profiled pass: device time by kernel class --------------------------------------
     lib.tnb_profile_enable(1)
-    sweep(psi, H)
+    # Jacobi sweeps per factorisation of this pass, by the number of columns k (the library reports the count of
+    # every tnb_svd_project call; the wrapper only records it)
+    from tncontract_b200 import devarray as _dv
+    sweeps_seen = []
+    _orig_svd_project = _dv.svd_project
+    def _recording_svd_project(a_):
+        out_ = _orig_svd_project(a_)
+        sweeps_seen.append((int(min(a_.shape[-2:])) if len(a_.shape) >= 2 else 1, int(_dv.last_svd_sweeps)))
+        return out_
+    _dv.svd_project = _recording_svd_project
+    try:
+        sweep(psi, H)
+    finally:
+        _dv.svd_project = _orig_svd_project
     torch.cuda.synchronize()
     import ctypes
     prof = {}
@@ -386,6 +399,13 @@ def main():
             roof["traffic_source"] = tr["source"]
     except (OSError, ValueError, KeyError):
         pass
+    if top == "jacobi_round" and sweeps_seen:
+        big = [n_ for k_, n_ in sweeps_seen if k_ >= 1024]
+        hist = {}
+        for n_ in big:
+            hist[str(n_)] = hist.get(str(n_), 0) + 1
+        roof["jacobi_sweeps"] = {"factorisations": len(sweeps_seen), "k1024_histogram": hist,
+                                 "k1024_mean": (sum(big) / len(big)) if big else None}
     roof["avg_launch_ms"] = per_launch_ms
     roof["launches_per_step"] = p["launches"]
     step_ms_prof = sum(v["ms"] for v in prof.values())
