@@ -141,8 +141,12 @@ int tnb_mps_mpo_site(const tnb_tensor_t* A, const tnb_tensor_t* W, void* out, vo
 
 /* ---- QR: np.linalg.qr(mode="reduced") (tensor.py:1044) ---------------------
  * A: m x n row-major (lda); Q: m x k, R: k x n contiguous, k = min(m,n).
- * Blocked Householder (compact WY); R has a real diagonal, sign convention
- * of LAPACK geqrf.  ws: tnb_qr_workspace() bytes. */
+ * k >= 128: block Gram-Schmidt with reorthogonalisation (BCGS-PIP+: every O(m n^2) step a DMMA
+ * GEMM, 64 x 64 Cholesky factors, device-side breakdown checks); k < 128 and as the fallback of
+ * the former: blocked Householder (compact WY, cluster panels).  R has a real diagonal -- positive
+ * on the Gram-Schmidt path, LAPACK geqrf's sign convention on the Householder path; Q R = A and
+ * Q^H Q = I either way (callers on the path only use the product and the isometry).
+ * ws: tnb_qr_workspace() bytes.  Synchronises `stream` once for k >= 128 (fallback flag). */
 size_t tnb_qr_workspace(int dtype, int64_t m, int64_t n);
 int tnb_qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
            void* Q, void* R, void* ws, size_t ws_bytes, void* stream);
