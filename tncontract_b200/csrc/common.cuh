@@ -209,6 +209,15 @@ struct PdlScope {
   explicit PdlScope(bool enable) : on(enable) { if (on) ++g_pdl; }
   ~PdlScope() { if (on) --g_pdl; }
 };
+// Device-side skip: kernels that take the flag (GEMM, split-K reduce, copy2d) return at once when *flag != 0.  The
+// lagged second pass of the Gram-Schmidt QR queues its update kernels inside a SkipScope and lets a device
+// predicate decide whether they run (no host round trip).
+extern thread_local const int* g_skip_flag;
+struct SkipScope {
+  const int* prev;
+  explicit SkipScope(const int* f) : prev(g_skip_flag) { g_skip_flag = f; }
+  ~SkipScope() { g_skip_flag = prev; }
+};
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};

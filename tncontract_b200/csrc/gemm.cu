@@ -50,6 +50,7 @@ struct GemmArgs {
   int splits;
   int64_t k_per_split;
   void* part;
+  const int* skip;   // device flag: the kernel returns at once when *skip != 0 (SkipScope), or null
 };
 
 template <bool CPLX, bool SMALL> struct Cfg;
@@ -116,6 +117,7 @@ gemm_kernel(GemmArgs g) {
   T* sB = sA + STAGES * LA::ELEMS;
   griddep_wait();               // no-ops unless launched with programmatic stream serialization (launch_k)
   griddep_launch_dependents();
+  if (g.skip && *g.skip) return;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, tq = lane & 3;  // fragment row / k index
@@ -344,6 +346,7 @@ __global__ void __launch_bounds__(256) gemm_tma_kernel(GemmArgs g, const __grid_
   __syncthreads();
   griddep_wait();               // barrier set-up above overlaps the tail of the previous kernel of a chain
   griddep_launch_dependents();
+  if (g.skip && *g.skip) return;
 
   double acc[MT][NT][6];
 #pragma unroll
@@ -565,6 +568,7 @@ __global__ void __launch_bounds__(256) gemm_tma_real_kernel(GemmArgs g, const __
   __syncthreads();
   griddep_wait();
   griddep_launch_dependents();
+  if (g.skip && *g.skip) return;
 
   double acc[MT][NT][2];
 #pragma unroll
@@ -697,9 +701,10 @@ static int try_gemm_tma_real(GemmArgs& g, bool a_kc, bool b_kc, int64_t batch, c
 // C = alpha * sum_z part[z] + beta * C  (deterministic: fixed summation order)
 template <typename T>
 __global__ void splitk_reduce_kernel(const T* part, int splits, int64_t M, int64_t N, T* C, int64_t ldc, double ar,
-                                     double ai, double br, double bi) {
+                                     double ai, double br, double bi, const int* skip) {
   griddep_wait();
   griddep_launch_dependents();
+  if (skip && *skip) return;
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   const bool has_beta = (br != 0.0 || bi != 0.0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += step) {
@@ -774,7 +779,8 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     return 0;
   }
   if (!A || !B) return TNB_E_ARG;
-  ProfScope prof(KC_GEMM, st, (cplx ? 8.0 : 2.0) * (double)M * (double)N * (double)K * (double)batch);
+  // (a product queued under a device-side skip flag may not execute: it is credited no work in the profile)
+  ProfScope prof(KC_GEMM, st, g_skip_flag ? 0.0 : (cplx ? 8.0 : 2.0) * (double)M * (double)N * (double)K * (double)batch);
   GemmArgs g;
   g.A = A; g.B = B; g.C = C;
   g.M = M; g.N = N; g.K = K;
@@ -782,6 +788,7 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
   g.sA = sA; g.sB = sB; g.sC = sC;
   g.alpha_r = ar; g.alpha_i = ai; g.beta_r = br; g.beta_i = bi;
   g.splits = 1; g.k_per_split = K; g.part = nullptr;
+  g.skip = g_skip_flag;
   g.conjA = cplx && (opA == TNB_OP_C || opA == TNB_OP_J);
   g.conjB = cplx && (opB == TNB_OP_C || opB == TNB_OP_J);
   // op N on A: stored M x K (k contiguous). op T/C: stored K x M (m contiguous).
@@ -832,8 +839,8 @@ int gemm_ws(int dtype, int opA, int opB, int64_t M, int64_t N, int64_t K, double
     if (rc != 0 || g.splits <= 1) return rc;
     int64_t blocks = (M * N + 255) / 256;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
-    if (cplx) TNB_CUDA_CHECK(launch_k(splitk_reduce_kernel<double2>, dim3((unsigned)blocks), dim3(256), 0, st, (const double2*)g.part, g.splits, M, N, (double2*)C, ldc, ar, ai, br, bi));
-    else TNB_CUDA_CHECK(launch_k(splitk_reduce_kernel<double>, dim3((unsigned)blocks), dim3(256), 0, st, (const double*)g.part, g.splits, M, N, (double*)C, ldc, ar, ai, br, bi));
+    if (cplx) TNB_CUDA_CHECK(launch_k(splitk_reduce_kernel<double2>, dim3((unsigned)blocks), dim3(256), 0, st, (const double2*)g.part, g.splits, M, N, (double2*)C, ldc, ar, ai, br, bi, g.skip));
+    else TNB_CUDA_CHECK(launch_k(splitk_reduce_kernel<double>, dim3((unsigned)blocks), dim3(256), 0, st, (const double*)g.part, g.splits, M, N, (double*)C, ldc, ar, ai, br, bi, g.skip));
     TNB_LAUNCH_CHECK();
     return 0;
   };

@@ -19,6 +19,7 @@ namespace tnb {
 
 std::atomic<long long> g_launches{0};
 thread_local int g_pdl = 0;
+thread_local const int* g_skip_flag = nullptr;
 // SM count of the CURRENT device, cached per device (a process may drive several GPUs, from several threads)
 int sm_count() {
   static std::atomic<int> cache[64];

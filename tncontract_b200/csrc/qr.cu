@@ -734,9 +734,10 @@ __global__ void pow2_scale_kernel(const unsigned long long* amax_bits, double* s
 // copy A (lda) -> W (ldw), contiguous rows, times scale[0] when given
 template <typename T>
 __global__ void copy2d_kernel(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows, int64_t cols,
-                              const double* scale) {
+                              const double* scale, const int* skip = nullptr) {
   griddep_wait();               // no-ops unless launched with programmatic stream serialization (launch_k)
   griddep_launch_dependents();
+  if (skip && *skip) return;    // device-side skip (SkipScope)
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   const double s = scale ? scale[0] : 1.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += step) {
@@ -867,6 +868,13 @@ struct QrLayout {
 
 constexpr int QR_CB = 64;   // column block of the Gram-Schmidt path (qr_bcgs2)
 constexpr int QR_GB = 256;  // column group of its lagged second pass; also the pitch of its panel buffers
+// A group whose Gram matrix against [earlier groups, itself] is within this of I after the FIRST pass is left as it is
+// (the update kernels of its second pass return at once): 1e-14 is the level of LAPACK's own Householder Q for these
+// sizes (eps sqrt(m) = 1.2e-14 at m = 3072).  Measured on the cfg 3 sweep: two groups in three qualify.
+#ifndef TNB_EXP_QR_SKIP_TOL
+#define TNB_EXP_QR_SKIP_TOL 1e-14
+#endif
+constexpr double QR_SKIP_TOL = TNB_EXP_QR_SKIP_TOL;
 
 static QrLayout qr_layout(int dtype, int64_t m, int64_t n) {
   QrLayout L;
@@ -1194,25 +1202,34 @@ constexpr int g_qr_overlap = TNB_EXP_QR_OVERLAP;
 // G = I + E (n x n Hermitian, upper triangle read) with |E| <= tol entrywise  ->  R = I + U, Rinv = I - U,
 // U = striu(E) + diag(E)/2: the Cholesky factor and its inverse to O(|E|^2).  Any entry outside tol (or a
 // NaN) raises flag[0]; the outputs stay finite either way.  Plain grid-stride kernel, any n.
+// C2 (jl x n, ld ldg, the rows above G: the couplings of the group to the earlier columns): when every entry of C2
+// and of E is within skip_tol -- the group came out of its first pass orthonormal to rounding level -- skip[0]
+// stays non-zero and the update kernels queued behind (SkipScope) return at once; any larger entry clears it.
 template <typename T>
 __global__ void near_identity_kernel(const T* G, int64_t ldg, int64_t n, T* R, int64_t ldr, T* Rinv, int64_t ldri,
-                                     double tol, int* flag) {
+                                     double tol, int* flag, const T* C2, int64_t jl, double skip_tol, int* skip) {
   typedef Num<T> N_;
   griddep_wait();
   griddep_launch_dependents();
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  bool bad = false;
+  bool bad = false, keep = false;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < jl * n; idx += step) {
+    const int64_t i = idx / n, j = idx - i * n;
+    if (!(N_::abs2(C2[i * ldg + j]) <= skip_tol * skip_tol)) keep = true;
+  }
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += step) {
     const int64_t i = idx / n, j = idx - i * n;
     T r = N_::zero(), ri = N_::zero();
     if (j > i) {
       const T e = G[i * ldg + j];
+      if (!(N_::abs2(e) <= skip_tol * skip_tol)) keep = true;
       if (!(N_::abs2(e) <= tol * tol)) bad = true;
       else { r = e; ri = N_::sub(N_::zero(), e); }
     } else if (j == i) {
       const T g = G[i * ldg + i];
       const T e = N_::sub(g, N_::one());
       double h = 0.0;
+      if (!(N_::abs2(e) <= skip_tol * skip_tol)) keep = true;
       if (!(N_::abs2(e) <= tol * tol)) bad = true;
       else h = 0.5 * (N_::real(g) - 1.0);
       r = N_::from(1.0 + h, 0.0);
@@ -1222,6 +1239,7 @@ __global__ void near_identity_kernel(const T* G, int64_t ldg, int64_t n, T* R, i
     Rinv[i * ldri + j] = ri;
   }
   if (bad) flag[0] = 1;
+  if (keep && skip) skip[0] = 0;
 }
 
 // returns 0 on success, 1 when the device flag asks for the Householder path, < 0 on errors
@@ -1260,6 +1278,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     if (rs) return rs;
   }
   int* flag = (int*)(base + L.off_sc + 128);
+  int* skipf = flag + 1;   // second pass of a group: non-zero = the group needs no update (see near_identity_kernel)
   double* sc = nullptr;
   if (scale_mode != 0) {
     unsigned long long* bits = (unsigned long long*)(base + L.off_sc);
@@ -1282,14 +1301,14 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
   }
   // the small factor of a pass: G (ld ldg) -> Rout (ld ldr), R^-1 -> Rinv (ld LDB)
   struct Factor { int kind; T* Rout; int64_t ldr; double rel_floor, abs_floor, near_tol; };
-  auto factorise = [&](const Factor& f, const T* G, int64_t ldg, T* Rinv, int64_t b) -> int {
+  auto factorise = [&](const Factor& f, const T* G, int64_t ldg, T* Rinv, int64_t b, int64_t jl) -> int {
     ProfScope prof(KC_QR_PANEL, st, (sizeof(T) == 16 ? 4.0 : 1.0) * 2.0 / 3.0 * (double)b * b * b);
     if (f.kind == 0) {
       TNB_CUDA_CHECK(launch_k(kern, dim3(1), dim3(CI_THREADS), ci_smem, st, G, ldg, (int)b, f.Rout, f.ldr, Rinv, LDB, f.rel_floor,
                               f.abs_floor, f.near_tol, flag));
     } else {
-      TNB_CUDA_CHECK(launch_k(near_identity_kernel<T>, dim3(blocks_for(b * b)), dim3(256), 0, st, G, ldg, b, f.Rout, f.ldr, Rinv,
-                              LDB, f.near_tol, flag));
+      TNB_CUDA_CHECK(launch_k(near_identity_kernel<T>, dim3(blocks_for((jl + b) * b)), dim3(256), 0, st, G, ldg, b, f.Rout,
+                              f.ldr, Rinv, LDB, f.near_tol, flag, (const T*)(G - jl * ldg), jl, QR_SKIP_TOL, skipf));
     }
     TNB_LAUNCH_CHECK();
     count_launch();
@@ -1315,7 +1334,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, b, b, jl, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, sk_main, st);
       if (r_) return r_;
     }
-    factorise(f, G, lds, Ri, b);
+    factorise(f, G, lds, Ri, b, jl);
     if (fork) {
       r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, jl, -1, 0, Qq, ldq, 0, S, lds, 0, 1, 0, Qp, ldq, 0, 1, sk_side, sk_side_bytes,
                    side.s);
@@ -1332,15 +1351,21 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, m, b, b, 1, 0, Qp, ldq, 0, Ri, LDB, 0, 0, 0, P2, LDB, 0, 1, st);
       if (r_) return r_;
     } else {
+      // (second pass of a group: these kernels return at once when the device predicate found nothing to correct)
+      SkipScope skip_scope(f.kind == 1 ? skipf : nullptr);
       if (jl > 0) {
         r_ = gemm(dtype, TNB_OP_N, TNB_OP_N, jl, b, b, -1, 0, S, lds, 0, Ri, LDB, 0, 0, 0, Bc, LDB, 0, 1, st);
         if (r_) return r_;
       }
       r_ = gemm_ws(dtype, TNB_OP_N, TNB_OP_N, m, b, kk, 1, 0, Qq, ldq, 0, Bc, LDB, 0, 0, 0, P2, LDB, 0, 1, sk, sk_main, st);
       if (r_) return r_;
+      TNB_CUDA_CHECK(launch_k(copy2d_kernel<T>, dim3(blocks_for(m * b)), dim3(256), 0, st, (const T*)P2, LDB, Qp, ldq, m, b,
+                              (const double*)nullptr, (const int*)g_skip_flag));
+      TNB_LAUNCH_CHECK();
+      return 0;
     }
     TNB_CUDA_CHECK(launch_k(copy2d_kernel<T>, dim3(blocks_for(m * b)), dim3(256), 0, st, (const T*)P2, LDB, Qp, ldq, m, b,
-                            (const double*)nullptr));
+                            (const double*)nullptr, (const int*)nullptr));
     TNB_LAUNCH_CHECK();
     return 0;
   };
@@ -1386,6 +1411,7 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
         TNB_CUDA_CHECK(cudaStreamWaitEvent(st, side.join2, 0));
         rfix_pending = false;
       }
+      TNB_CUDA_CHECK(cudaMemsetAsync(skipf, 1, sizeof(int), st));   // non-zero until an entry beyond QR_SKIP_TOL clears it
       rc = pass(0, g0, bg, Qb + g0, Sb, LDB, Factor{1, R2, LDB, 0.0, 0.0, 1e-8});
       if (rc) return rc;
       // R[G, G] = R2 R1g,  R[:g0, G] = C1 + C2 R1g   (R1g = the group's first-pass factor, now in R[G, G]).
@@ -1398,13 +1424,16 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
         sr = side.s;
       }
       T* Rgg = Rg + g0 * n + g0;
-      copy2d_kernel<T><<<blocks_for(bg * bg), 256, 0, sr>>>(Rgg, n, Rt, LDB, bg, bg, nullptr);
-      TNB_LAUNCH_CHECK();
-      rc = gemm(dtype, TNB_OP_N, TNB_OP_N, bg, bg, bg, 1, 0, R2, LDB, 0, Rt, LDB, 0, 0, 0, Rgg, n, 0, 1, sr);
-      if (rc) return rc;
-      if (g0 > 0) {
-        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, g0, bg, bg, 1, 0, Sb, LDB, 0, Rt, LDB, 0, 1, 0, Rg + g0, n, 0, 1, sr);
+      {
+        SkipScope skip_scope(skipf);   // an untouched group keeps its first-pass R
+        copy2d_kernel<T><<<blocks_for(bg * bg), 256, 0, sr>>>(Rgg, n, Rt, LDB, bg, bg, nullptr, skipf);
+        TNB_LAUNCH_CHECK();
+        rc = gemm(dtype, TNB_OP_N, TNB_OP_N, bg, bg, bg, 1, 0, R2, LDB, 0, Rt, LDB, 0, 0, 0, Rgg, n, 0, 1, sr);
         if (rc) return rc;
+        if (g0 > 0) {
+          rc = gemm(dtype, TNB_OP_N, TNB_OP_N, g0, bg, bg, 1, 0, Sb, LDB, 0, Rt, LDB, 0, 1, 0, Rg + g0, n, 0, 1, sr);
+          if (rc) return rc;
+        }
       }
       if (overlap) {
         TNB_CUDA_CHECK(cudaEventRecord(side.join2, side.s));
