@@ -9,6 +9,12 @@ a = rn(1100, 330)                      # m >= 1024: split-K scratch, side stream
 q, r = dv.qr(dv.DevArray.from_host(a))
 q, r = np.asarray(q), np.asarray(r)
 print("qr", np.linalg.norm(q @ r - a) / np.linalg.norm(a), np.linalg.norm(q.conj().T @ q - np.eye(330)))
+# graded columns (cond ~ 1e3): the first pass leaves |G - I| ~ eps cond^2 >> 1e-14, so the second pass of the groups is NOT skipped
+g = rn(1100, 330) * np.logspace(0, -3, 330)[None, :]
+g = g @ np.linalg.qr(rn(330, 330))[0]
+q, r = dv.qr(dv.DevArray.from_host(g))
+q, r = np.asarray(q), np.asarray(r)
+print("qr graded", np.linalg.norm(q @ r - g) / np.linalg.norm(g), np.linalg.norm(q.conj().T @ q - np.eye(330)))
 b = rn(300, 200)
 q, r = dv.qr(dv.DevArray.from_host(b))
 print("qr small", np.linalg.norm(np.asarray(q) @ np.asarray(r) - b) / np.linalg.norm(b))

@@ -333,6 +333,34 @@ def test_qr_many_columns(cplx):
         check(a, tol=1e-11)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_qr_second_pass_skip(cplx):
+    """Lagged Gram-Schmidt QR (qr.cu, m >= 1024, several 256-column groups): a group whose first pass left it
+    orthonormal to 1e-14 entrywise keeps its first-pass columns (the update kernels of its second pass return
+    at once on a device flag), every other group is corrected.  Either way no entry of Q^H Q - I may exceed the
+    skip tolerance (plus the rounding of this test's own product), and R must be LAPACK's up to row signs."""
+    torch, _lib, dv = _mods()
+    rng = np.random.default_rng(41)
+    m, n = 1536, 768
+    well = rnd(rng, (m, n), cplx)                       # groups come out of the first pass at rounding level
+    u, _ = np.linalg.qr(rnd(rng, (m, n), cplx))
+    v, _ = np.linalg.qr(rnd(rng, (n, n), cplx))
+    graded = (u * np.logspace(0, -3, n)[None, :]) @ v.conj().T   # cond 1e3: |G - I| ~ eps cond^2 >> 1e-14, corrected
+    mixed = np.concatenate([well[:, :256], graded[:, :256], well[:, 256:512]], axis=1)  # both kinds in one call
+    for name, a in (("well", well), ("graded", graded), ("mixed", mixed)):
+        q, r = dv.qr(dv.DevArray.from_host(a))
+        q, r = np.asarray(q), np.asarray(r)
+        assert rel(q @ r, a) < TOL, name
+        e = np.abs(q.conj().T @ q - np.eye(n))
+        assert e.max() < 3e-14, (name, e.max())
+        rr = np.linalg.qr(a, mode="r")
+        assert rel(np.abs(np.diag(r)), np.abs(np.diag(rr))) < 1e-11, name
+        # the same factorisation twice gives the same bits (the device predicate is deterministic)
+        q2, r2 = dv.qr(dv.DevArray.from_host(a))
+        assert np.array_equal(np.asarray(q2), q) and np.array_equal(np.asarray(r2), r), name
+
+
 
 @pytest.mark.gpu
 def test_get_into_host_buffer():
@@ -495,6 +523,28 @@ def test_svd_1024_columns(cplx):
     sref = np.linalg.svd(g, compute_uv=False)
     assert np.max(np.abs(np.asarray(s) - sref) / sref) < 1e-8
     assert np.linalg.norm(np.asarray(u).conj().T @ np.asarray(u) - np.eye(1024)) < 1e-9
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_svd_project_rank_deficient(cplx):
+    """Projection SVD of rank-deficient matrices (the boundary matrices of BASELINE.json config 5 and the sites of
+    config 2 -- a random positive MPS is numerically of rank ~1 -- are of this kind).  The reference's truncation
+    keeps whatever np.linalg.svd reports above 1e-15 (tensor.py:1146-1150), noise directions included, and relies on
+    their vectors being orthonormal: U must be an isometry over ALL k columns, not only the live ones.  (A floor
+    under which columns are left unrotated was tried for the sweep count -- cfg 5: 23 -> 19 sweeps per 4096 x 4096
+    matrix -- and dropped because it breaks exactly this.)"""
+    torch, _lib, dv = _mods()
+    rng = np.random.default_rng(23)
+    for m, n, r in [(300, 260, 90), (260, 300, 200), (520, 512, 17)]:
+        a = rnd(rng, (m, r), cplx) @ rnd(rng, (r, n), cplx)
+        u, s, p = dv.svd_project(dv.DevArray.from_host(a))
+        u, s, p = np.asarray(u), np.asarray(s), np.asarray(p)
+        k = min(m, n)
+        sref = np.linalg.svd(a, compute_uv=False)
+        assert np.max(np.abs(s - sref)) <= 1e-12 * sref[0], (m, n, r)
+        assert rel(u @ p, a) < 1e-12, (m, n, r)
+        assert int(np.sum(s > 1e-12 * s[0])) == r, (m, n, r)
+        assert np.max(np.abs(u.conj().T @ u - np.eye(k))) < 1e-11, (m, n, r)
 
 
 @pytest.mark.parametrize("cplx", [False, True])
