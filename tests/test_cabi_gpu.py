@@ -538,6 +538,7 @@ def test_svd_project_rank_deficient(cplx):
     for m, n, r in [(300, 260, 90), (260, 300, 200), (520, 512, 17)]:
         a = rnd(rng, (m, r), cplx) @ rnd(rng, (r, n), cplx)
         u, s, p = dv.svd_project(dv.DevArray.from_host(a))
+        sweeps = int(dv.last_svd_sweeps)
         u, s, p = np.asarray(u), np.asarray(s), np.asarray(p)
         k = min(m, n)
         sref = np.linalg.svd(a, compute_uv=False)
@@ -545,6 +546,9 @@ def test_svd_project_rank_deficient(cplx):
         assert rel(u @ p, a) < 1e-12, (m, n, r)
         assert int(np.sum(s > 1e-12 * s[0])) == r, (m, n, r)
         assert np.max(np.abs(u.conj().T @ u - np.eye(k))) < 1e-11, (m, n, r)
+        # Jacobi runs on R^H (wide) or on R2^H of the second QR (tall / square): the null space does not hold the
+        # sweeps up (on the columns of R itself these matrices took 23-24 sweeps)
+        assert sweeps <= 14, (m, n, r, sweeps)
 
 
 @pytest.mark.parametrize("cplx", [False, True])

@@ -1226,10 +1226,30 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
     rc = qr(dtype, n, m, AH, m, proj ? (void*)nullptr : (void*)Q, R, qr_ws, 2, &qscale, st);
     if (rc) return rc;
   }
-  // Jacobi orthogonalises the columns of X, stored as rows of Xt:
-  //   X = R^H (Xt = conj(R)) -- except for a tall matrix in projection mode, where the LEFT vectors
-  //   are wanted from the column space of R itself: X = R (Xt = R^T).
-  const bool x_is_r = proj && !wide;
+  // Jacobi orthogonalises the columns of X, stored as rows of Xt: X = R^H (Xt = conj(R)) -- the rows of a triangular
+  // factor are graded by the QR, its columns are not, and Jacobi converges on the former (Drmac-Veselic).
+  // A tall (or square) matrix in projection mode wants the LEFT vectors of R without accumulating V.  Jacobi on the
+  // columns of R itself delivers them (Y = R V, Ur = Y / sigma) but converges badly: 12 sweeps where R^H needs 10 on a
+  // random matrix, and 24-30 where it needs 8-11 when A is rank-deficient -- the null space of R's columns only
+  // emerges through cancellation, rotation by rotation (cfg 5's 4096 x 4096 boundary matrices: 23 sweeps; cfg 2's
+  // numerically rank-one sites).  So R is factored once more, R^H = Q2 R2: R = R2^H Q2^H has the left vectors of
+  // X = R2^H, whose columns are the graded rows of R2 (NumPy emulation, scratch/jacobi_emul.py: 30 -> 8 sweeps on a
+  // rank-90 300 x 260 matrix, U an isometry over all columns to 4e-15).  Q2 is never formed.
+#ifdef TNB_EXP_NO_SECOND_QR
+  const bool x_is_r = proj && !wide;   // kernel experiments: Jacobi on the columns of R itself (Xt = R^T)
+#else
+  const bool x_is_r = false;
+  if (proj && !wide) {
+    const int64_t sh[2] = {k, k}, is_h[2] = {1, k};
+    rc = permute_view(dtype, R, 2, sh, is_h, Vt, 1.0, 0.0, 1, st);   // Vt (free in projection mode) <- R^H
+    if (rc) return rc;
+    // the scale factors of the first QR live in its workspace, which the second one reuses
+    TNB_CUDA_CHECK(cudaMemcpyAsync(nrm + 2, qscale, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    qscale = nrm + 2;
+    rc = qr(dtype, k, k, Vt, k, nullptr, R, qr_ws, 0, nullptr, st);   // R <- R2
+    if (rc) return rc;
+  }
+#endif
   {
     const int64_t sh[2] = {k, k};
     const int64_t is_conj[2] = {k, 1}, is_tr[2] = {1, k};
@@ -1287,7 +1307,7 @@ static int svd_impl(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, (T*)U, k, k, k, 0, 1, 1);
       TNB_LAUNCH_CHECK();
     } else {
-      // A = Q R, R V = Y = Ur Sigma:  U = Q Ur, with Ur^T = sorted rows of Yt / sigma (kept in Vs)
+      // A = Q R, R = R2^H Q2^H, R2^H V = Y = Ur Sigma:  U = Q Ur, with Ur^T = sorted rows of Yt / sigma (kept in Vs)
       gather_rows_kernel<T><<<blocks_for(k * k), 256, 0, st>>>(Xt, k, perm, sig, Vs, k, k, k, 0, 1, 0);
       TNB_LAUNCH_CHECK();
       rc = gemm(dtype, TNB_OP_N, TNB_OP_T, m, k, k, 1, 0, Q, k, 0, Vs, k, 0, 0, 0, U, k, 0, 1, st);
