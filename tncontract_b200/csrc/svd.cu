@@ -10,7 +10,9 @@
 //   2. One-sided (Hestenes) block Jacobi on X = R^H:  X V = Y with mutually
 //      orthogonal columns, so R^H = Y V^H.  Working on R^H rather than R is the
 //      Drmac-Veselic preconditioning: its columns are much closer to
-//      orthogonal and the sweep count drops.
+//      orthogonal and the sweep count drops.  (Projection mode of a tall or
+//      square matrix needs the LEFT vectors of R: it factors R^H = Q2 R2 once
+//      more and runs on X = R2^H -- see svd_impl.)
 //   3. sigma_j = |Y[:, j]|, sorted on the device; U / Vh assembled with one
 //      DMMA GEMM (Q V) and one gather/scale kernel (Y / sigma).
 //
