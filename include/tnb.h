@@ -142,7 +142,8 @@ int tnb_mps_mpo_site(const tnb_tensor_t* A, const tnb_tensor_t* W, void* out, vo
 /* ---- QR: np.linalg.qr(mode="reduced") (tensor.py:1044) ---------------------
  * A: m x n row-major (lda); Q: m x k, R: k x n contiguous, k = min(m,n).
  * k >= 128: block Gram-Schmidt with reorthogonalisation (BCGS-PIP+: every O(m n^2) step a DMMA
- * GEMM, 64 x 64 Cholesky factors, device-side breakdown checks); k < 128 and as the fallback of
+ * GEMM, 64 x 64 Cholesky factors, device-side breakdown checks; the second pass runs per group of 256
+ * columns and is skipped on the device for a group its first pass left orthonormal to 1e-14 entrywise); k < 128 and as the fallback of
  * the former: blocked Householder (compact WY, cluster panels).  R has a real diagonal -- positive
  * on the Gram-Schmidt path, LAPACK geqrf's sign convention on the Householder path; Q R = A and
  * Q^H Q = I either way (callers on the path only use the product and the isometry).
@@ -154,8 +155,9 @@ int tnb_qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
 /* ---- SVD: np.linalg.svd(full_matrices=False) (tensor.py:915) ---------------
  * A: m x n row-major (lda); U: m x k, S: k doubles (descending), Vh: k x n,
  * k = min(m,n).  QR/LQ pre-reduction + block one-sided Jacobi.  Synchronises
- * the stream once per Jacobi sweep (convergence flag).  Returns TNB_E_NOCONV
- * if max_sweeps is exhausted. */
+ * the stream once per batch of queued Jacobi sweeps (convergence flag; the first batch is as long as the
+ * previous factorisation needed, so normally once per call).  Returns TNB_E_NOCONV
+ * if max_sweeps is exhausted or the input holds NaN / Inf. */
 size_t tnb_svd_workspace(int dtype, int64_t m, int64_t n);
 int tnb_svd(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
             void* U, double* S, void* Vh, void* ws, size_t ws_bytes, int* sweeps_out, void* stream);
@@ -163,6 +165,9 @@ int tnb_svd(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
 /* Projection form used by the MPS sweeps (onedim_core.py:317-351): U and S as above, and
  * P = U^H A = diag(S) Vh (k x n) -- the product the sweep absorbs into the next site.  V is never
  * accumulated (one third fewer Jacobi flops); the rows of P carry an absolute error of eps |A|.
+ * A wide matrix (m < n) takes U from Jacobi on R^H of A^H = Q R; a tall or square one factors R^H = Q2 R2 once
+ * more and runs on R2^H, which has the left vectors of R (Jacobi on the columns of R itself needs 2-4 x the sweeps
+ * on rank-deficient input).  U is an isometry over all k columns, noise directions included.
  * Same workspace as tnb_svd. */
 int tnb_svd_project(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
                     void* U, double* S, void* P, void* ws, size_t ws_bytes, int* sweeps_out, void* stream);
