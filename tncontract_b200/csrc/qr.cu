@@ -1172,6 +1172,68 @@ __global__ void __launch_bounds__(CI_THREADS) chol_inv_kernel(const T* G, int64_
   }
 }
 
+
+// G <- G - C^H C for the first pass of a 64-column block (Pythagorean step of BCGS-PIP): C is jl x b (ld ldc, the
+// couplings of the block to the jl earlier columns), G is b x b Hermitian (ld ldg; only its UPPER triangle is
+// read by the factorisation kernels, and only that is updated).  One CTA per upper 8 x 8 tile; its 16 warps split
+// the jl rows of C (eight k-steps of loads in flight per warp), partial tiles are summed in warp order
+// (deterministic): one launch instead of a split-K GEMM and its reduce kernel on the chain of every block.
+constexpr int GC_WARPS = 16, GC_UNR = 8;
+template <typename T>
+__global__ void __launch_bounds__(GC_WARPS * 32) gram_correct_kernel(const T* C, int64_t ldc, int64_t jl, T* G, int64_t ldg, int b) {
+  typedef Num<T> N_;
+  constexpr bool CPLX = sizeof(T) == 16;
+  griddep_wait();
+  griddep_launch_dependents();
+  const int nt = (b + 7) / 8;
+  int mi = 0, rem = blockIdx.x;          // tile (mi <= nj) of the upper triangle, row-major
+  while (rem >= nt - mi) { rem -= nt - mi; ++mi; }
+  const int nj = mi + rem;
+  const int I0 = mi * 8, K0 = nj * 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  // rows of C per warp: a multiple of 4 (the DMMA k)
+  const int64_t per = ((jl + GC_WARPS * 4 - 1) / (GC_WARPS * 4)) * 4;
+  const int64_t p_beg = (int64_t)warp * per, p_end = (p_beg + per < jl) ? p_beg + per : jl;
+  const bool ci_ok = I0 + gq < b, ck_ok = K0 + gq < b;
+  double acc[CPLX ? 4 : 2] = {};
+  for (int64_t p0 = p_beg; p0 < p_end; p0 += 4 * GC_UNR) {
+    T a[GC_UNR], q[GC_UNR];
+#pragma unroll
+    for (int u = 0; u < GC_UNR; ++u) {
+      const int64_t p = p0 + 4 * u + tq;
+      a[u] = (p < p_end && ci_ok) ? N_::conj(C[p * ldc + I0 + gq]) : N_::zero();
+      q[u] = (p < p_end && ck_ok) ? C[p * ldc + K0 + gq] : N_::zero();
+    }
+#pragma unroll
+    for (int u = 0; u < GC_UNR; ++u) {
+      if constexpr (CPLX) {
+        dmma884(acc[0], acc[1], a[u].x, q[u].x);
+        dmma884(acc[0], acc[1], -a[u].y, q[u].y);
+        dmma884(acc[2], acc[3], a[u].x, q[u].y);
+        dmma884(acc[2], acc[3], a[u].y, q[u].x);
+      } else {
+        dmma884(acc[0], acc[1], a[u], q[u]);
+      }
+    }
+  }
+  __shared__ T part[GC_WARPS][64];
+  {
+    T* d = &part[warp][gq * 8 + 2 * tq];
+    if constexpr (CPLX) { d[0] = make_double2(acc[0], acc[2]); d[1] = make_double2(acc[1], acc[3]); }
+    else { d[0] = acc[0]; d[1] = acc[1]; }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int i = I0 + (tid >> 3), k = K0 + (tid & 7);
+    if (i < b && k < b && k >= i) {
+      T sum = part[0][tid];
+#pragma unroll
+      for (int w = 1; w < GC_WARPS; ++w) sum = N_::add(sum, part[w][tid]);
+      G[(int64_t)i * ldg + k] = N_::sub(G[(int64_t)i * ldg + k], sum);
+    }
+  }
+}
+
 template <typename T>
 __global__ void scale_by_kernel(T* x, int64_t n, const double* s) {
   const double f = s[0];
@@ -1330,6 +1392,16 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       TNB_CUDA_CHECK(cudaEventRecord(side.fork, st));
       TNB_CUDA_CHECK(cudaStreamWaitEvent(side.s, side.fork, 0));
     }
+#ifndef TNB_EXP_QR_GEMM_GCORR
+    if (jl > 0 && f.kind == 0 && b <= QR_CB) {
+      // first pass of a block: the 64 x 64 correction in one launch (only the upper triangle, which is all chol_inv_kernel reads)
+      ProfScope prof(KC_GEMM, st, (sizeof(T) == 16 ? 8.0 : 2.0) * (double)b * (double)b * (double)jl * 0.5);
+      const int nt = (int)((b + 7) / 8);
+      TNB_CUDA_CHECK(launch_k(gram_correct_kernel<T>, dim3((unsigned)(nt * (nt + 1) / 2)), dim3(GC_WARPS * 32), 0, st, (const T*)S,
+                              lds, jl, G, lds, (int)b));
+      TNB_LAUNCH_CHECK();
+    } else
+#endif
     if (jl > 0) {
       r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, b, b, jl, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, sk_main, st);
       if (r_) return r_;
