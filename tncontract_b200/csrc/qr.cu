@@ -1267,31 +1267,52 @@ constexpr int g_qr_overlap = TNB_EXP_QR_OVERLAP;
 // C2 (jl x n, ld ldg, the rows above G: the couplings of the group to the earlier columns): when every entry of C2
 // and of E is within skip_tol -- the group came out of its first pass orthonormal to rounding level -- skip[0]
 // stays non-zero and the update kernels queued behind (SkipScope) return at once; any larger entry clears it.
+// The skip predicate of a group's second pass, evaluated on what the S product left: C2 (jl x n, ld ldg, the couplings
+// to the earlier columns) and G0 = W^H W (n x n, upper triangle).  Every entry of C2 and of G0 - I within skip_tol
+// leaves skip[0] non-zero (set by the caller); any larger entry (or a NaN) clears it.  Runs BEFORE the Pythagorean
+// correction G0 - C2^H C2, which is itself skipped with the rest (for a group that passes it is ~1e-28).
 template <typename T>
-__global__ void near_identity_kernel(const T* G, int64_t ldg, int64_t n, T* R, int64_t ldr, T* Rinv, int64_t ldri,
-                                     double tol, int* flag, const T* C2, int64_t jl, double skip_tol, int* skip) {
+__global__ void skip_predicate_kernel(const T* G0, int64_t ldg, int64_t n, const T* C2, int64_t jl, double skip_tol, int* skip) {
   typedef Num<T> N_;
   griddep_wait();
   griddep_launch_dependents();
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  bool bad = false, keep = false;
+  const double t2 = skip_tol * skip_tol;
+  bool keep = false;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < jl * n; idx += step) {
     const int64_t i = idx / n, j = idx - i * n;
-    if (!(N_::abs2(C2[i * ldg + j]) <= skip_tol * skip_tol)) keep = true;
+    if (!(N_::abs2(C2[i * ldg + j]) <= t2)) keep = true;
   }
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += step) {
+    const int64_t i = idx / n, j = idx - i * n;
+    if (j < i) continue;
+    const T g = G0[i * ldg + j];
+    const T e = (j == i) ? N_::sub(g, N_::one()) : g;
+    if (!(N_::abs2(e) <= t2)) keep = true;
+  }
+  if (keep) skip[0] = 0;
+}
+
+template <typename T>
+__global__ void near_identity_kernel(const T* G, int64_t ldg, int64_t n, T* R, int64_t ldr, T* Rinv, int64_t ldri,
+                                     double tol, int* flag, const int* skip) {
+  typedef Num<T> N_;
+  griddep_wait();
+  griddep_launch_dependents();
+  if (skip && *skip) return;   // the group needs no second pass: nobody reads R / Rinv
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += step) {
     const int64_t i = idx / n, j = idx - i * n;
     T r = N_::zero(), ri = N_::zero();
     if (j > i) {
       const T e = G[i * ldg + j];
-      if (!(N_::abs2(e) <= skip_tol * skip_tol)) keep = true;
       if (!(N_::abs2(e) <= tol * tol)) bad = true;
       else { r = e; ri = N_::sub(N_::zero(), e); }
     } else if (j == i) {
       const T g = G[i * ldg + i];
       const T e = N_::sub(g, N_::one());
       double h = 0.0;
-      if (!(N_::abs2(e) <= skip_tol * skip_tol)) keep = true;
       if (!(N_::abs2(e) <= tol * tol)) bad = true;
       else h = 0.5 * (N_::real(g) - 1.0);
       r = N_::from(1.0 + h, 0.0);
@@ -1301,7 +1322,6 @@ __global__ void near_identity_kernel(const T* G, int64_t ldg, int64_t n, T* R, i
     Rinv[i * ldri + j] = ri;
   }
   if (bad) flag[0] = 1;
-  if (keep && skip) skip[0] = 0;
 }
 
 // returns 0 on success, 1 when the device flag asks for the Householder path, < 0 on errors
@@ -1369,8 +1389,8 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       TNB_CUDA_CHECK(launch_k(kern, dim3(1), dim3(CI_THREADS), ci_smem, st, G, ldg, (int)b, f.Rout, f.ldr, Rinv, LDB, f.rel_floor,
                               f.abs_floor, f.near_tol, flag));
     } else {
-      TNB_CUDA_CHECK(launch_k(near_identity_kernel<T>, dim3(blocks_for((jl + b) * b)), dim3(256), 0, st, G, ldg, b, f.Rout,
-                              f.ldr, Rinv, LDB, f.near_tol, flag, (const T*)(G - jl * ldg), jl, QR_SKIP_TOL, skipf));
+      TNB_CUDA_CHECK(launch_k(near_identity_kernel<T>, dim3(blocks_for(b * b)), dim3(256), 0, st, G, ldg, b, f.Rout,
+                              f.ldr, Rinv, LDB, f.near_tol, flag, (const int*)skipf));
     }
     TNB_LAUNCH_CHECK();
     count_launch();
@@ -1392,17 +1412,27 @@ static int qr_bcgs2(int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
       TNB_CUDA_CHECK(cudaEventRecord(side.fork, st));
       TNB_CUDA_CHECK(cudaStreamWaitEvent(side.s, side.fork, 0));
     }
+    if (f.kind == 1) {
+      // second pass of a group: decide on the device whether there is anything to correct; the correction of G, the
+      // factor and every update kernel behind them return at once when there is not
+      TNB_CUDA_CHECK(launch_k(skip_predicate_kernel<T>, dim3(blocks_for((jl + b) * b)), dim3(256), 0, st, (const T*)G, lds, b,
+                              (const T*)S, jl, QR_SKIP_TOL, skipf));
+      TNB_LAUNCH_CHECK();
+    }
+    bool corrected = (jl == 0);
 #ifndef TNB_EXP_QR_GEMM_GCORR
-    if (jl > 0 && f.kind == 0 && b <= QR_CB) {
+    if (!corrected && f.kind == 0 && b <= QR_CB) {
       // first pass of a block: the 64 x 64 correction in one launch (only the upper triangle, which is all chol_inv_kernel reads)
       ProfScope prof(KC_GEMM, st, (sizeof(T) == 16 ? 8.0 : 2.0) * (double)b * (double)b * (double)jl * 0.5);
       const int nt = (int)((b + 7) / 8);
       TNB_CUDA_CHECK(launch_k(gram_correct_kernel<T>, dim3((unsigned)(nt * (nt + 1) / 2)), dim3(GC_WARPS * 32), 0, st, (const T*)S,
                               lds, jl, G, lds, (int)b));
       TNB_LAUNCH_CHECK();
-    } else
+      corrected = true;
+    }
 #endif
-    if (jl > 0) {
+    if (!corrected) {
+      SkipScope skip_scope(f.kind == 1 ? skipf : nullptr);
       r_ = gemm_ws(dtype, TNB_OP_C, TNB_OP_N, b, b, jl, -1, 0, S, lds, 0, S, lds, 0, 1, 0, G, lds, 0, 1, sk, sk_main, st);
       if (r_) return r_;
     }
