@@ -549,6 +549,16 @@ def test_svd_project_rank_deficient(cplx):
         # Jacobi runs on R^H (wide) or on R2^H of the second QR (tall / square): the null space does not hold the
         # sweeps up (on the columns of R itself these matrices took 23-24 sweeps)
         assert sweeps <= 14, (m, n, r, sweeps)
+    # degenerate inputs of the tall / square path (second QR of R^H): zero matrix, identity, a single column
+    z = np.zeros((8, 5), dtype=complex if cplx else float)
+    u, s, p = dv.svd_project(dv.DevArray.from_host(z))
+    assert np.array_equal(np.asarray(s), np.zeros(5)) and np.all(np.isfinite(np.asarray(u))) and np.all(np.asarray(p) == 0)
+    e = np.eye(70, dtype=complex if cplx else float)
+    u, s, p = dv.svd_project(dv.DevArray.from_host(e))
+    assert np.max(np.abs(np.asarray(s) - 1)) < 1e-14 and rel(np.asarray(u) @ np.asarray(p), e) < 1e-14
+    c = rnd(rng, (200, 1), cplx)
+    u, s, p = dv.svd_project(dv.DevArray.from_host(c))
+    assert abs(np.asarray(s)[0] - np.linalg.norm(c)) < 1e-13 * np.linalg.norm(c) and rel(np.asarray(u) @ np.asarray(p), c) < 1e-14
 
 
 @pytest.mark.parametrize("cplx", [False, True])
